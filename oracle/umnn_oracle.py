@@ -1,0 +1,404 @@
+"""CPU oracle for the UMNN Clenshaw-Curtis integration hot path (numpy restatement).
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``umnn_b200/`` or ``models/`` may import
+this module; only ``tests/``, ``__graft_entry__.smoke()`` and the CPU-baseline /
+``--impl reference`` legs of ``bench.py`` use it, and there only as the checker or
+as the CPU arm that is timed beside the GPU path.
+
+Every function restates, in plain numpy, the algorithm of a reference function
+(AWehenkel/UMNN @ 59118c14) and cites the ``file:line`` it follows.  The
+restatement is PINNED: ``tests/golden/make_golden.py`` imports the real reference
+from ``/root/reference`` in the build container, runs it on seeded inputs and
+commits the outputs under ``tests/golden/``; ``tests/test_oracle_golden.py``
+checks this module against those vectors on every CPU test run.
+
+Conventions
+-----------
+* ``Q`` = ``nb_steps``; there are ``Q + 1`` quadrature nodes.
+* parameters travel as one flat fp32 vector in ``nn.Sequential`` order
+  ``W1 (out x in, row-major), b1, W2, b2, ...`` -- the order of
+  ``_flatten(integrand.parameters())`` (ParallelNeuralIntegral.py:6-8).
+* flow layout ("strided"): ``x[N, D]``, ``h[N, E*D]`` with ``h[n, e*D + d]`` the
+  e-th context value of slot (n, d)                         (UMNNMAF.py:263-284)
+* contiguous layout: ``x[N, 1]``, ``h[N, E]``               (MonotonicNN.py:26-27)
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+LEAKY_SLOPE = 0.01  # nn.LeakyReLU() default, UMNNMAF.py:250
+
+HIDDEN_RELU = "relu"          # IntegrandNN, MonotonicNN.py:17-21
+HIDDEN_LEAKY = "leaky_relu"   # IntegrandNetwork, UMNNMAF.py:246-251
+OUT_ELU_PLUS_1 = "elu_plus_1"  # ELUPlus UMNNMAF.py:11-16, and nn.ELU()+1. MonotonicNN.py:23,27
+OUT_SIGMOID = "sigmoid"        # dict_act_func["Sigmoid"], UMNNMAF.py:19
+
+
+# ----------------------------------------------------------------------------
+# a1: Clenshaw-Curtis nodes and weights
+# ----------------------------------------------------------------------------
+def cc_nodes_weights(Q: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Weights ``w[Q+1]`` and nodes ``t[Q+1]`` (both float32, node 0 = +1, node Q = -1).
+
+    Follows compute_cc_weights, ParallelNeuralIntegral.py:14-34 (same as
+    NeuralIntegral.py:14-34 and UMNNMAF.py:55-69): a float64 cosine matrix
+    ``cos(k*i*pi/Q)`` whose first column is replaced by 1/2 and whose last column is
+    halved, scaled by 2/Q, contracted against the even-moment vector
+    ``2/(1-k^2)`` (k even, with the k=0 entry set to 1) and rounded to float32.
+    """
+    idx = np.arange(Q + 1, dtype=np.int64)
+    cosmat = np.cos(np.outer(idx, idx).astype(np.float64) * math.pi / Q)  # [k, i]
+    cosmat[:, 0] = 0.5
+    cosmat[:, Q] = 0.5 * cosmat[:, Q]
+    cosmat = cosmat * 2 / Q
+    moments = np.zeros(Q + 1, dtype=np.float64)
+    even = idx[idx % 2 == 0]
+    moments[even] = 2.0 / (1.0 - even.astype(np.float64) ** 2)
+    moments[0] = 1.0
+    w = (cosmat.T @ moments.reshape(-1, 1)).reshape(-1)
+    t = np.cos(idx.astype(np.float64) * math.pi / Q)
+    return w.astype(np.float32), t.astype(np.float32)
+
+
+# ----------------------------------------------------------------------------
+# parameter handling
+# ----------------------------------------------------------------------------
+@dataclass
+class MLPSpec:
+    """Shape of an integrand MLP: widths = [n_in, H1, ..., HL, 1]."""
+    widths: Tuple[int, ...]
+    hidden_act: str = HIDDEN_LEAKY
+    out_act: str = OUT_ELU_PLUS_1
+
+    @property
+    def n_params(self) -> int:
+        return sum(i * o + o for i, o in zip(self.widths[:-1], self.widths[1:]))
+
+
+def unpack_params(spec: MLPSpec, flat: np.ndarray) -> List[Tuple[np.ndarray, np.ndarray]]:
+    """Split the flat vector into [(W_l [out, in], b_l [out])] views."""
+    flat = np.asarray(flat).reshape(-1)
+    assert flat.size == spec.n_params, (flat.size, spec.n_params)
+    out, off = [], 0
+    for n_in, n_out in zip(spec.widths[:-1], spec.widths[1:]):
+        W = flat[off:off + n_in * n_out].reshape(n_out, n_in)
+        off += n_in * n_out
+        b = flat[off:off + n_out]
+        off += n_out
+        out.append((W, b))
+    return out
+
+
+def _hidden_act(v: np.ndarray, kind: str) -> np.ndarray:
+    if kind == HIDDEN_LEAKY:
+        return np.where(v > 0, v, v * v.dtype.type(LEAKY_SLOPE))
+    if kind == HIDDEN_RELU:
+        return np.maximum(v, v.dtype.type(0))
+    raise ValueError(kind)
+
+
+def _hidden_act_grad(v: np.ndarray, kind: str) -> np.ndarray:
+    if kind == HIDDEN_LEAKY:
+        return np.where(v > 0, v.dtype.type(1), v.dtype.type(LEAKY_SLOPE))
+    if kind == HIDDEN_RELU:
+        return (v > 0).astype(v.dtype)
+    raise ValueError(kind)
+
+
+def _out_act(v: np.ndarray, kind: str) -> np.ndarray:
+    one = v.dtype.type(1)
+    if kind == OUT_ELU_PLUS_1:
+        # nn.ELU(alpha=1) then "+ 1." in the working precision: the negative branch is
+        # expm1(v) + 1, which is quantised at 2^-24 in fp32 and exactly 0 for v <~ -17.3.
+        return np.where(v > 0, v, np.expm1(np.minimum(v, 0))) + one
+    if kind == OUT_SIGMOID:
+        return one / (one + np.exp(-v))
+    raise ValueError(kind)
+
+
+def _out_act_grad(v: np.ndarray, kind: str) -> np.ndarray:
+    one = v.dtype.type(1)
+    if kind == OUT_ELU_PLUS_1:
+        # torch elu_backward with is_result=False: grad * alpha * exp(x) for x <= 0
+        return np.where(v > 0, one, np.exp(np.minimum(v, 0)))
+    if kind == OUT_SIGMOID:
+        s = one / (one + np.exp(-v))
+        return s * (one - s)
+    raise ValueError(kind)
+
+
+def mlp_rows(spec: MLPSpec, flat: np.ndarray, rows: np.ndarray, keep: bool = False):
+    """Apply the integrand MLP to ``rows[R, n_in]`` -> ``[R]``.
+
+    The nn.Sequential of IntegrandNetwork (UMNNMAF.py:245-254) / IntegrandNN
+    (MonotonicNN.py:15-24): Linear, act, ..., Linear, output activation.
+    With ``keep`` the pre-activations are returned for the backward pass.
+    """
+    a = rows
+    pre = []
+    layers = unpack_params(spec, flat)
+    for li, (W, b) in enumerate(layers):
+        v = a @ W.T.astype(a.dtype) + b.astype(a.dtype)
+        if keep:
+            pre.append((a, v))
+        a = _hidden_act(v, spec.hidden_act) if li < len(layers) - 1 else _out_act(v, spec.out_act)
+    out = a.reshape(-1)
+    return (out, pre) if keep else out
+
+
+# ----------------------------------------------------------------------------
+# a4 / a5: integrand networks
+# ----------------------------------------------------------------------------
+def slot_inputs_strided(x: np.ndarray, h: np.ndarray) -> np.ndarray:
+    """[N, D], [N, E*D] -> [N*D, 1+E]: row (n, d) = [x[n,d], h[n,0*D+d], ..., h[n,(E-1)*D+d]].
+
+    IntegrandNetwork.forward, UMNNMAF.py:263-281: cat, view(N, 1+E, D), transpose(1,2).
+    """
+    N, D = x.shape
+    E = h.shape[1] // D
+    assert h.shape[1] == E * D
+    stacked = np.concatenate([x[:, None, :], h.reshape(N, E, D)], axis=1)  # [N, 1+E, D]
+    return np.ascontiguousarray(stacked.transpose(0, 2, 1)).reshape(N * D, 1 + E)
+
+
+def integrand_network(spec: MLPSpec, flat: np.ndarray, x: np.ndarray, h: np.ndarray) -> np.ndarray:
+    """IntegrandNetwork.forward(x, h) -> [N, D], UMNNMAF.py:263-284."""
+    N, D = x.shape
+    return mlp_rows(spec, flat, slot_inputs_strided(x, h)).reshape(N, D)
+
+
+def integrand_nn(spec: MLPSpec, flat: np.ndarray, x: np.ndarray, h: np.ndarray) -> np.ndarray:
+    """IntegrandNN.forward(x, h) -> [N, 1], MonotonicNN.py:26-27 (cat(x,h) -> net -> +1)."""
+    return mlp_rows(spec, flat, np.concatenate([x, h], axis=1)).reshape(-1, 1)
+
+
+def _integrand(spec, flat, x, h, layout):
+    return integrand_network(spec, flat, x, h) if layout == "strided" else integrand_nn(spec, flat, x, h)
+
+
+# ----------------------------------------------------------------------------
+# a2 / a3 / a6: the integral (forward)
+# ----------------------------------------------------------------------------
+def _limits(x0: np.ndarray, x: np.ndarray, Q: int):
+    """step = (x-x0)/Q (ParallelNeuralIntegral.py:102); xT = x0 + Q*step (:49)."""
+    dt = x.dtype.type
+    step = (x - x0) / dt(Q)
+    xT = x0 + dt(Q) * step
+    return xT
+
+
+def integrate_parallel(spec: MLPSpec, flat: np.ndarray, x0: np.ndarray, x: np.ndarray, h: np.ndarray,
+                       Q: int, layout: str = "strided", chunk: int = 0) -> np.ndarray:
+    """ParallelNeuralIntegral.forward -> integrate(...), ParallelNeuralIntegral.py:37-65,99-108.
+
+    All Q+1 nodes of every sample are laid out as rows (sample-major, node-minor),
+    the integrand is applied once, the result is weighted and summed over the node
+    axis, then scaled by (xT - x0)/2.  ``chunk`` > 0 processes that many samples at
+    a time (memory only; results are per-sample independent).
+    """
+    w, t = cc_nodes_weights(Q)
+    dt = x.dtype.type
+    w = w.astype(x.dtype)
+    t = t.astype(x.dtype)
+    B, Dx = x.shape
+    out = np.empty_like(x)
+    step = chunk if chunk > 0 else B
+    for s in range(0, B, step):
+        sl = slice(s, min(B, s + step))
+        x0c, hc = x0[sl], h[sl]
+        xT = _limits(x0c, x[sl], Q)
+        n = xT.shape[0]
+        nodes = x0c[:, None, :] + (xT - x0c)[:, None, :] * (t[None, :, None] + dt(1)) / dt(2)  # [n, Q+1, Dx]
+        h_rep = np.broadcast_to(hc[:, None, :], (n, Q + 1, hc.shape[1])).reshape(n * (Q + 1), -1)
+        f = _integrand(spec, flat, nodes.reshape(n * (Q + 1), Dx), h_rep, layout).reshape(n, Q + 1, Dx)
+        z = (f * w[None, :, None]).sum(axis=1)
+        out[sl] = z * (xT - x0c) / dt(2)
+    return out
+
+
+def integrate_sequential(spec: MLPSpec, flat: np.ndarray, x0: np.ndarray, x: np.ndarray, h: np.ndarray,
+                         Q: int, layout: str = "strided") -> np.ndarray:
+    """NeuralIntegral.forward -> integrate(...), NeuralIntegral.py:37-66,80-88 (node loop)."""
+    w, t = cc_nodes_weights(Q)
+    dt = x.dtype.type
+    xT = _limits(x0, x, Q)
+    z = np.zeros_like(x)
+    for i in range(Q + 1):
+        xi = x0 + (xT - x0) * (dt(t[i]) + dt(1)) / dt(2)
+        z = z + dt(w[i]) * _integrand(spec, flat, xi, h, layout)
+    return z * (xT - x0) / dt(2)
+
+
+# ----------------------------------------------------------------------------
+# a7 / a8: backward (Leibniz rule)
+# ----------------------------------------------------------------------------
+def mlp_rows_vjp(spec: MLPSpec, flat: np.ndarray, rows: np.ndarray, cot: np.ndarray):
+    """Vector-Jacobian product of ``mlp_rows``: returns (d_flat [P], d_rows [R, n_in]).
+
+    Manual restatement of what torch.autograd.grad(f, params / h, cot) evaluates in
+    computeIntegrand, ParallelNeuralIntegral.py:83-94.
+    """
+    _, pre = mlp_rows(spec, flat, rows, keep=True)
+    layers = unpack_params(spec, flat)
+    grads = []
+    delta = cot.reshape(-1, 1).astype(rows.dtype)
+    for li in range(len(layers) - 1, -1, -1):
+        a_in, v = pre[li]
+        if li == len(layers) - 1:
+            delta = delta * _out_act_grad(v, spec.out_act)
+        else:
+            delta = delta * _hidden_act_grad(v, spec.hidden_act)
+        gW = delta.T @ a_in
+        gb = delta.sum(axis=0)
+        grads.append((gW, gb))
+        delta = delta @ layers[li][0].astype(rows.dtype)
+    grads.reverse()
+    d_flat = np.concatenate([np.concatenate([gW.reshape(-1), gb.reshape(-1)]) for gW, gb in grads])
+    return d_flat, delta
+
+
+def integral_backward(spec: MLPSpec, flat: np.ndarray, x0: np.ndarray, x: np.ndarray, h: np.ndarray,
+                      grad_out: np.ndarray, Q: int, layout: str = "strided", chunk: int = 0):
+    """ParallelNeuralIntegral.backward, ParallelNeuralIntegral.py:110-123 with
+    integrate(compute_grad=True) :66-80 and computeIntegrand :83-94.
+
+    Returns (d_x0, d_x, d_flat_params, d_h).
+    """
+    w, t = cc_nodes_weights(Q)
+    dt = x.dtype.type
+    w = w.astype(x.dtype)
+    t = t.astype(x.dtype)
+    B, Dx = x.shape
+    d_flat = np.zeros(spec.n_params, dtype=x.dtype)
+    d_h = np.zeros_like(h)
+    step = chunk if chunk > 0 else B
+    for s in range(0, B, step):
+        sl = slice(s, min(B, s + step))
+        x0c, hc, g = x0[sl], h[sl], grad_out[sl]
+        xT = _limits(x0c, x[sl], Q)
+        n = xT.shape[0]
+        x_tot = g * (xT - x0c) / dt(2)                                   # :70
+        cot = x_tot[:, None, :] * w[None, :, None]                       # :71  [n, Q+1, Dx]
+        nodes = x0c[:, None, :] + (xT - x0c)[:, None, :] * (t[None, :, None] + dt(1)) / dt(2)
+        if layout == "strided":
+            E = hc.shape[1] // Dx
+            h_rep = np.broadcast_to(hc[:, None, :], (n, Q + 1, hc.shape[1])).reshape(n * (Q + 1), -1)
+            rows = slot_inputs_strided(nodes.reshape(n * (Q + 1), Dx), h_rep)     # [(n*(Q+1))*Dx, 1+E]
+            gp, d_rows = mlp_rows_vjp(spec, flat, rows, cot.reshape(-1))
+            # d_rows[:, 1:] is the gradient wrt the context of slot (n, i, d); sum over nodes i,
+            # and map back to h[n, e*D + d]                               (:92-94)
+            dctx = d_rows[:, 1:].reshape(n, Q + 1, Dx, E).sum(axis=1)     # [n, Dx, E]
+            d_h[sl] = dctx.transpose(0, 2, 1).reshape(n, E * Dx)
+        else:
+            h_rep = np.broadcast_to(hc[:, None, :], (n, Q + 1, hc.shape[1])).reshape(n * (Q + 1), -1)
+            rows = np.concatenate([nodes.reshape(n * (Q + 1), 1), h_rep], axis=1)
+            gp, d_rows = mlp_rows_vjp(spec, flat, rows, cot.reshape(-1))
+            d_h[sl] = d_rows[:, 1:].reshape(n, Q + 1, -1).sum(axis=1)
+        d_flat += gp
+    d_x = _integrand(spec, flat, x, h, layout) * grad_out                # :115,:123
+    d_x0 = -_integrand(spec, flat, x0, h, layout) * grad_out             # :116,:123
+    return d_x0, d_x, d_flat, d_h
+
+
+# ----------------------------------------------------------------------------
+# MADE conditioner (produces h); only what the flow path needs
+# ----------------------------------------------------------------------------
+def made_masks(nin: int, hidden: Sequence[int], nout: int) -> List[np.ndarray]:
+    """Masks of MADE(natural_ordering=True, random=False), made.py:74-105.
+
+    Returned in (in, out) orientation as built there; MaskedLinear stores the transpose.
+    """
+    L = len(hidden)
+    m = {-1: np.arange(nin)}
+    for l in range(L):
+        m[l] = np.array([nin - 1 - (i % nin) for i in range(hidden[l])])
+    masks = [m[l - 1][:, None] <= m[l][None, :] for l in range(L)]
+    masks.append(m[L - 1][:, None] < m[-1][None, :])
+    if nout > nin:
+        masks[-1] = np.concatenate([masks[-1]] * (nout // nin), axis=1)
+    return masks
+
+
+def made_forward(nin: int, hidden: Sequence[int], nout: int, weights: Sequence[Tuple[np.ndarray, np.ndarray]],
+                 x: np.ndarray) -> np.ndarray:
+    """MADE.forward for nout != 2: masked Linear / ReLU stack, made.py:26-27,53-62,113-119."""
+    masks = made_masks(nin, hidden, nout)
+    a = x
+    for li, ((W, b), mk) in enumerate(zip(weights, masks)):
+        a = a @ (W * mk.T.astype(W.dtype)).T.astype(a.dtype) + b.astype(a.dtype)
+        if li < len(weights) - 1:
+            a = np.maximum(a, a.dtype.type(0))
+    return a
+
+
+# ----------------------------------------------------------------------------
+# a9 / a10 / a11: one flow block and the stacked log-likelihood
+# ----------------------------------------------------------------------------
+def umnnmaf_forward(spec, flat, x, h, Q, scaling=None):
+    """UMNNMAF.forward with x0 = 0: z = exp(scaling) * (integral + z0), UMNNMAF.py:76-134;
+    z0 is the first E-chunk of h (:80)."""
+    D = x.shape[1]
+    z0 = h[:, :D]
+    integ = integrate_parallel(spec, flat, np.zeros_like(x), x, h, Q, "strided")
+    s = np.exp(np.zeros(D, dtype=x.dtype) if scaling is None else scaling.astype(x.dtype))
+    return s[None, :] * (integ + z0)
+
+
+def umnnmaf_log_jac(spec, flat, x, h, scaling=None):
+    """UMNNMAF.compute_log_jac: log(f(x,h) + 1e-10) + scaling, UMNNMAF.py:136-139."""
+    D = x.shape[1]
+    sc = np.zeros(D, dtype=x.dtype) if scaling is None else scaling.astype(x.dtype)
+    jac = integrand_network(spec, flat, x, h)
+    return np.log(jac + x.dtype.type(1e-10)) + sc[None, :]
+
+
+def flow_compute_ll(blocks, x, Q):
+    """UMNNMAFFlow.compute_ll, UMNNMAFFlow.py:109-119.
+
+    ``blocks`` is a list of dicts {spec, flat, made: (nin, hidden, nout, weights)}.
+    Returns (ll [B], z [B, D]).
+    """
+    dt = x.dtype.type
+    log_jac = np.zeros_like(x)
+    z = x
+    for blk in blocks:
+        nin, hid, nout, mw = blk["made"]
+        h = made_forward(nin, hid, nout, mw, x)
+        z = umnnmaf_forward(blk["spec"], blk["flat"], x, h, Q)[:, ::-1]
+        log_jac = log_jac + umnnmaf_log_jac(blk["spec"], blk["flat"], x, h)
+        x = z
+    z = z[:, ::-1]
+    pi32 = np.float32(math.pi).astype(x.dtype)
+    log_prob_gauss = (dt(-0.5) * (np.log(pi32 * dt(2)) + z ** 2)).sum(axis=1)
+    return log_jac.sum(axis=1) + log_prob_gauss, np.ascontiguousarray(z)
+
+
+# ----------------------------------------------------------------------------
+# seeded synthetic data shared by the golden generator, the tests and the bench
+# ----------------------------------------------------------------------------
+def synth_params(spec: MLPSpec, seed: int, gain: float = 1.0) -> np.ndarray:
+    """nn.Linear-like init U(-1/sqrt(in), 1/sqrt(in)) from the frozen RandomState stream.
+
+    ``gain`` > 1 gives the "trained-like" variant (ELU goes negative, kinks exercised).
+    """
+    rng = np.random.RandomState(seed)
+    parts = []
+    for n_in, n_out in zip(spec.widths[:-1], spec.widths[1:]):
+        k = 1.0 / math.sqrt(n_in)
+        parts.append(rng.uniform(-k, k, size=n_in * n_out) * gain)
+        parts.append(rng.uniform(-k, k, size=n_out) * gain)
+    return np.concatenate(parts).astype(np.float32)
+
+
+def synth_inputs(B: int, Dx: int, Hh: int, seed: int, x0_zero: bool = True):
+    """x ~ 2*N(0,1), h ~ N(0,1), grad_out ~ N(0,1), x0 = 0 or 0.5*N(0,1)."""
+    rng = np.random.RandomState(seed)
+    x = (2.0 * rng.standard_normal((B, Dx))).astype(np.float32)
+    h = rng.standard_normal((B, Hh)).astype(np.float32)
+    g = rng.standard_normal((B, Dx)).astype(np.float32)
+    x0 = np.zeros((B, Dx), np.float32) if x0_zero else (0.5 * rng.standard_normal((B, Dx))).astype(np.float32)
+    return x0, x, h, g
