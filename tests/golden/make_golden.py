@@ -182,6 +182,13 @@ def run_flow():
         lj = model.compute_log_jac(torch.from_numpy(xn.copy()))
     stored["z_forward_eval"] = z_eval.numpy()
     stored["log_jac_eval"] = lj.numpy()
+    # sampling direction: UMNNMAFFlow.invert on the first 4 latent vectors (5 refinement rounds)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        x_back = model.invert(torch.from_numpy(stored["z"][:4].copy()), iter=5)
+    stored["invert_x"] = x_back.numpy()
+    stored["invert_x_true"] = xn[:4]
     np.savez_compressed(os.path.join(HERE, "flow_ll.npz"), **stored)
     print("flow_ll: ll[:3] =", stored["ll"][:3])
 

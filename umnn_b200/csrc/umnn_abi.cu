@@ -1,0 +1,239 @@
+// extern "C" entry points declared in include/umnn_b200.h: argument validation, dispatch to the
+// kernels, error strings.  No torch types; plain pointers and sizes only.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "umnn_common.cuh"
+
+namespace umnn {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    (void)cudaGetLastError();  // clear the sticky-free error state
+    return (int)e;
+}
+
+int validate_desc(const umnn_desc* d) {
+    if (!d) { set_error("desc is NULL"); return UMNN_ERR_NULL; }
+    if (d->abi_version != UMNN_ABI_VERSION) {
+        set_error("desc.abi_version=%d, library is %d", d->abi_version, UMNN_ABI_VERSION);
+        return UMNN_ERR_ABI;
+    }
+    if (d->layout != UMNN_LAYOUT_STRIDED_D && d->layout != UMNN_LAYOUT_CONTIG) {
+        set_error("desc.layout=%d is not a UMNN_LAYOUT_*", d->layout); return UMNN_ERR_DESC;
+    }
+    if (d->n_samples < 0 || d->n_dims < 1) {
+        set_error("desc.n_samples=%lld / n_dims=%d out of range", (long long)d->n_samples, d->n_dims); return UMNN_ERR_DESC;
+    }
+    if (d->layout == UMNN_LAYOUT_CONTIG && d->n_dims != 1) {
+        set_error("UMNN_LAYOUT_CONTIG requires n_dims == 1 (got %d)", d->n_dims); return UMNN_ERR_DESC;
+    }
+    if (d->n_ctx < 0 || d->n_ctx + 1 > UMNN_MAX_WIDTH) {
+        set_error("desc.n_ctx=%d out of range [0, %d]", d->n_ctx, UMNN_MAX_WIDTH - 1); return UMNN_ERR_DESC;
+    }
+    if (d->n_layers < 2 || d->n_layers > UMNN_MAX_LAYERS) {
+        set_error("desc.n_layers=%d out of range [2, %d]", d->n_layers, UMNN_MAX_LAYERS); return UMNN_ERR_DESC;
+    }
+    if (d->widths[0] != d->n_ctx + 1) {
+        set_error("desc.widths[0]=%d must equal 1 + n_ctx = %d", d->widths[0], d->n_ctx + 1); return UMNN_ERR_DESC;
+    }
+    if (d->widths[d->n_layers] != 1) {
+        set_error("desc.widths[n_layers]=%d must be 1", d->widths[d->n_layers]); return UMNN_ERR_DESC;
+    }
+    for (int l = 1; l < d->n_layers; ++l)
+        if (d->widths[l] < 1 || d->widths[l] > UMNN_MAX_WIDTH) {
+            set_error("desc.widths[%d]=%d out of range [1, %d]", l, d->widths[l], UMNN_MAX_WIDTH); return UMNN_ERR_DESC;
+        }
+    if (d->hidden_act != UMNN_ACT_RELU && d->hidden_act != UMNN_ACT_LEAKY_RELU) {
+        set_error("desc.hidden_act=%d is not a UMNN_ACT_*", d->hidden_act); return UMNN_ERR_DESC;
+    }
+    if (d->out_act != UMNN_OUT_ELU_PLUS_1 && d->out_act != UMNN_OUT_SIGMOID) {
+        set_error("desc.out_act=%d is not a UMNN_OUT_*", d->out_act); return UMNN_ERR_DESC;
+    }
+    if (d->nb_steps < 1 || d->nb_steps > UMNN_MAX_STEPS) {
+        set_error("desc.nb_steps=%d out of range [1, %d]", d->nb_steps, UMNN_MAX_STEPS); return UMNN_ERR_DESC;
+    }
+    if (d->precision != UMNN_PREC_FP32 && d->precision != UMNN_PREC_BF16X3 && d->precision != UMNN_PREC_AUTO) {
+        set_error("desc.precision=%d is not a UMNN_PREC_*", d->precision); return UMNN_ERR_DESC;
+    }
+    if ((long long)d->n_samples * d->n_dims > (1LL << 40)) {
+        set_error("n_samples * n_dims too large"); return UMNN_ERR_DESC;
+    }
+    return 0;
+}
+
+// Which kernel family serves this descriptor.  UMNN_PREC_AUTO resolves to FP32 until the BF16x3
+// tensor-core kernel covers the shape.
+static int resolve_precision(const umnn_desc* d) {
+    if (d->precision == UMNN_PREC_AUTO) return UMNN_PREC_FP32;
+    return d->precision;
+}
+
+}  // namespace umnn
+
+using namespace umnn;
+
+extern "C" {
+
+int umnn_abi_version(void) { return UMNN_ABI_VERSION; }
+
+const char* umnn_last_error(void) { return g_err; }
+
+int umnn_cc_tables(int32_t Q, float* nodes_host, float* weights_host) {
+    if (!nodes_host || !weights_host) { set_error("umnn_cc_tables: NULL output"); return UMNN_ERR_NULL; }
+    if (Q < 1 || Q > UMNN_MAX_STEPS) { set_error("umnn_cc_tables: nb_steps=%d out of range", Q); return UMNN_ERR_DESC; }
+    // w_i = sum_{k even} m_k * c_{k,i},  c_{k,i} = (2/Q) cos(k i pi / Q) with column 0 -> 1/Q (cos replaced by
+    // 1/2) and column Q halved; m_0 = 1, m_k = 2/(1-k^2).          ParallelNeuralIntegral.py:19-30
+    const double pi = 3.14159265358979323846;
+    for (int i = 0; i <= Q; ++i) {
+        double acc = 0.0;
+        for (int k = 0; k <= Q; k += 2) {
+            double c;
+            if (i == 0) c = 0.5;
+            else c = cos((double)k * (double)i * pi / (double)Q);
+            if (i == Q) c = 0.5 * c;
+            c = c * 2.0 / (double)Q;
+            const double m = (k == 0) ? 1.0 : 2.0 / (1.0 - (double)k * (double)k);
+            acc += c * m;
+        }
+        weights_host[i] = (float)acc;
+        nodes_host[i] = (float)cos((double)i * pi / (double)Q);
+    }
+    return 0;
+}
+
+int64_t umnn_param_count(const umnn_desc* d) {
+    if (validate_desc(d) != 0) return -1;
+    int64_t n = 0;
+    for (int l = 0; l < d->n_layers; ++l) n += (int64_t)d->widths[l] * d->widths[l + 1] + d->widths[l + 1];
+    return n;
+}
+
+size_t umnn_packed_params_bytes(const umnn_desc* d) {
+    if (validate_desc(d) != 0) return 0;
+    switch (resolve_precision(d)) {
+        case UMNN_PREC_FP32: return sizeof(float) * (size_t)make_fp32_layout(d).total_floats;
+        default: return 0;
+    }
+}
+
+int umnn_pack_params(const umnn_desc* d, const float* flat_params, void* params_packed, void* stream) {
+    int rc = validate_desc(d);
+    if (rc) return rc;
+    if (!flat_params || !params_packed) { set_error("umnn_pack_params: NULL pointer"); return UMNN_ERR_NULL; }
+    switch (resolve_precision(d)) {
+        case UMNN_PREC_FP32:
+            return launch_pack_fp32(d, flat_params, (float*)params_packed, (cudaStream_t)stream);
+        default:
+            set_error("umnn_pack_params: precision %d is not available for this shape", d->precision);
+            return UMNN_ERR_UNSUPPORTED;
+    }
+}
+
+size_t umnn_workspace_bytes(const umnn_desc* d, int32_t for_backward) {
+    if (validate_desc(d) != 0) return 0;
+    (void)for_backward;
+    return 0;
+}
+
+int umnn_cc_forward(const umnn_desc* d, const float* x0, const float* x, const float* h, const void* params_packed,
+                    const float* nodes, const float* weights, float* out_integral, float* out_f_at_x,
+                    float* out_f_at_x0, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = validate_desc(d);
+    if (rc) return rc;
+    (void)workspace; (void)workspace_bytes;
+    if (d->n_samples == 0) return 0;
+    if (!x || !params_packed || !nodes || !weights || !out_integral || (d->n_ctx > 0 && !h)) {
+        set_error("umnn_cc_forward: required pointer is NULL"); return UMNN_ERR_NULL;
+    }
+    switch (resolve_precision(d)) {
+        case UMNN_PREC_FP32:
+            return launch_forward_fp32(d, x0, x, h, (const float*)params_packed, nodes, weights, out_integral,
+                                       out_f_at_x, out_f_at_x0, (cudaStream_t)stream);
+        default:
+            set_error("umnn_cc_forward: precision %d is not available for this shape", d->precision);
+            return UMNN_ERR_UNSUPPORTED;
+    }
+}
+
+int umnn_cc_backward(const umnn_desc* d, const float* x0, const float* x, const float* h, const void* params_packed,
+                     const float* nodes, const float* weights, const float* grad_out, const float* grad_f_at_x,
+                     float* d_x0, float* d_x, float* d_h, float* d_params, void* workspace, size_t workspace_bytes,
+                     void* stream) {
+    int rc = validate_desc(d);
+    if (rc) return rc;
+    (void)x0; (void)x; (void)h; (void)params_packed; (void)nodes; (void)weights; (void)grad_out; (void)grad_f_at_x;
+    (void)d_x0; (void)d_x; (void)d_h; (void)d_params; (void)workspace; (void)workspace_bytes; (void)stream;
+    set_error("umnn_cc_backward: not built yet");
+    return UMNN_ERR_UNSUPPORTED;
+}
+
+int umnn_cc_forward_host(const umnn_desc* d, const float* x0_host, const float* x_host, const float* h_host,
+                         const float* flat_params_host, float* out_integral_host, float* out_f_at_x_host,
+                         float* out_f_at_x0_host, int32_t device) {
+    int rc = validate_desc(d);
+    if (rc) return rc;
+    if (d->n_samples == 0) return 0;
+    if (!x_host || !flat_params_host || !out_integral_host || (d->n_ctx > 0 && !h_host)) {
+        set_error("umnn_cc_forward_host: required pointer is NULL"); return UMNN_ERR_NULL;
+    }
+    UMNN_CUDA_TRY(cudaSetDevice(device));
+    const size_t n_slots = (size_t)d->n_samples * d->n_dims;
+    const size_t xb = n_slots * sizeof(float);
+    const size_t hb = (size_t)d->n_samples * d->n_dims * d->n_ctx * sizeof(float);
+    const size_t pb = (size_t)umnn_param_count(d) * sizeof(float);
+    const size_t packed_b = umnn_packed_params_bytes(d);
+    const int Q = d->nb_steps;
+    std::vector<float> tabs(2 * (Q + 1));
+    rc = umnn_cc_tables(Q, tabs.data(), tabs.data() + Q + 1);
+    if (rc) return rc;
+
+    // one slab: x0 | x | h | flat | packed | tables | out | fx | fx0   (each 256-byte aligned)
+    auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+    const size_t o_x0 = 0, o_x = o_x0 + al(xb), o_h = o_x + al(xb), o_p = o_h + al(hb), o_pk = o_p + al(pb),
+                 o_t = o_pk + al(packed_b), o_out = o_t + al(tabs.size() * sizeof(float)), o_fx = o_out + al(xb),
+                 o_fx0 = o_fx + al(xb), total = o_fx0 + al(xb);
+    char* slab = nullptr;
+    UMNN_CUDA_TRY(cudaMalloc((void**)&slab, total));
+    cudaStream_t s = 0;
+    auto fail = [&](int code) { cudaFree(slab); return code; };
+#define UMNN_HOST_TRY(expr)                                                       \
+    do {                                                                          \
+        cudaError_t _e = (expr);                                                  \
+        if (_e != cudaSuccess) return fail(::umnn::cuda_fail(_e, #expr));         \
+    } while (0)
+    if (x0_host) UMNN_HOST_TRY(cudaMemcpyAsync(slab + o_x0, x0_host, xb, cudaMemcpyHostToDevice, s));
+    UMNN_HOST_TRY(cudaMemcpyAsync(slab + o_x, x_host, xb, cudaMemcpyHostToDevice, s));
+    if (hb) UMNN_HOST_TRY(cudaMemcpyAsync(slab + o_h, h_host, hb, cudaMemcpyHostToDevice, s));
+    UMNN_HOST_TRY(cudaMemcpyAsync(slab + o_p, flat_params_host, pb, cudaMemcpyHostToDevice, s));
+    UMNN_HOST_TRY(cudaMemcpyAsync(slab + o_t, tabs.data(), tabs.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+    rc = umnn_pack_params(d, (const float*)(slab + o_p), slab + o_pk, s);
+    if (rc) return fail(rc);
+    rc = umnn_cc_forward(d, x0_host ? (const float*)(slab + o_x0) : nullptr, (const float*)(slab + o_x),
+                         (const float*)(slab + o_h), slab + o_pk, (const float*)(slab + o_t),
+                         (const float*)(slab + o_t) + Q + 1, (float*)(slab + o_out),
+                         out_f_at_x_host ? (float*)(slab + o_fx) : nullptr,
+                         out_f_at_x0_host ? (float*)(slab + o_fx0) : nullptr, nullptr, 0, s);
+    if (rc) return fail(rc);
+    UMNN_HOST_TRY(cudaMemcpyAsync(out_integral_host, slab + o_out, xb, cudaMemcpyDeviceToHost, s));
+    if (out_f_at_x_host) UMNN_HOST_TRY(cudaMemcpyAsync(out_f_at_x_host, slab + o_fx, xb, cudaMemcpyDeviceToHost, s));
+    if (out_f_at_x0_host) UMNN_HOST_TRY(cudaMemcpyAsync(out_f_at_x0_host, slab + o_fx0, xb, cudaMemcpyDeviceToHost, s));
+    UMNN_HOST_TRY(cudaStreamSynchronize(s));
+#undef UMNN_HOST_TRY
+    cudaFree(slab);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,285 @@
+"""The neural integral: autograd Functions, the device-agnostic torch path and the kernel dispatcher.
+
+Behavioural spec (AWehenkel/UMNN @ 59118c14), written fresh:
+  * models/UMNN/ParallelNeuralIntegral.py  -- integrate :37-80, computeIntegrand :83-94,
+    ParallelNeuralIntegral :97-123
+  * models/UMNN/NeuralIntegral.py          -- integrate :37-66, computeIntegrand :69-75,
+    NeuralIntegral :78-99
+
+Two routes serve the same maths:
+  kernel route   CUDA float32 tensors + a recognised integrand (IntegrandNetwork, IntegrandNN,
+                 ContiguousIntegrand) + inv_f == False + not tracing  ->  ONE fused sm_100a launch
+                 through the C ABI (umnn_b200/_native.py).  If the native library is missing this
+                 raises; it never degrades to torch ops.
+  torch route    everything else the public API allows: arbitrary callables / lambdas, CPU or MPS
+                 tensors, float64, TorchScript tracing, inv_f=True.  Same results as the reference.
+"""
+from __future__ import annotations
+
+import os
+import warnings
+from typing import Optional, Tuple
+
+import torch
+
+from . import kernel
+from .networks import _flatten  # noqa: F401  (re-exported: the reference modules expose it)
+from .quadrature import compute_cc_weights, device_tables
+
+# rows (= samples x nodes x dims) the torch route evaluates at once during a backward pass;
+# above this the batch is processed in chunks (gradients are sums over independent samples)
+_TORCH_ROUTE_MAX_ROWS = int(os.environ.get("UMNN_B200_TORCH_ROUTE_MAX_ROWS", 1 << 22))
+
+
+# --------------------------------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------------------------------
+def _tables_for(x0: torch.Tensor, nb_steps: int, cc_weights=None, steps=None):
+    """[Q+1] weight / node vectors on x0's device."""
+    if cc_weights is None or steps is None:
+        if x0.is_cuda:
+            return device_tables(nb_steps, x0.device)
+        cc_weights, steps = compute_cc_weights(nb_steps)
+    return cc_weights.to(x0.device).view(-1), steps.to(x0.device).view(-1)
+
+
+def _node_rows(x0, xT, h, nodes):
+    """Abscissae [B*(Q+1), Dx] and replicated context [B*(Q+1), Hh], sample-major / node-minor."""
+    n = nodes.shape[0]
+    span = xT - x0
+    X = x0.unsqueeze(1) + span.unsqueeze(1) * (nodes.view(1, n, 1) + 1) / 2
+    H = h.unsqueeze(1).expand(-1, n, -1)
+    return X.reshape(-1, x0.shape[1]), H.reshape(-1, h.shape[1])
+
+
+def _params_of(integrand):
+    get = getattr(integrand, "parameters", None)
+    return list(get()) if callable(get) else []
+
+
+def _call(integrand, x, h):
+    fwd = getattr(integrand, "forward", None)
+    return fwd(x, h) if callable(fwd) else integrand(x, h)
+
+
+# --------------------------------------------------------------------------------------------------
+# torch route, vectorised over the nodes ("parallel")
+# --------------------------------------------------------------------------------------------------
+def integrate(x0, nb_steps, step_sizes, integrand, h, compute_grad=False, x_tot=None, inv_f=False,
+              cc_weights=None, steps=None):
+    """Clenshaw-Curtis quadrature of `integrand` from x0 to x0 + nb_steps*step_sizes.
+
+    compute_grad=False: returns the integral [B, Dx].
+    compute_grad=True : returns (grad wrt flattened integrand parameters, grad wrt h) for the
+                        cotangent x_tot [B, Dx] of the integral.
+    """
+    w, t = _tables_for(x0, nb_steps, cc_weights, steps)
+    xT = x0 + nb_steps * step_sizes
+    B, n = x0.shape[0], nb_steps + 1
+    X, H = _node_rows(x0, xT, h, t)
+    if not compute_grad:
+        f = integrand(X, H)
+        if inv_f:
+            f = 1 / f
+        z = (f.view(B, n, -1) * w.view(1, n, 1)).sum(1)
+        return z * (xT - x0) / 2
+    cot = (x_tot * (xT - x0) / 2).unsqueeze(1) * w.view(1, n, 1)
+    return computeIntegrand(X, H, integrand, cot.reshape(B * n, -1), n, inv_f=inv_f)
+
+
+def computeIntegrand(x, h, integrand, x_tot, nb_steps, inv_f=False):
+    """VJP of the integrand rows: (flat parameter gradient, context gradient summed over nodes)."""
+    h = h.detach().requires_grad_(True) if not h.requires_grad else h
+    with torch.enable_grad():
+        f = _call(integrand, x, h)
+        if inv_f:
+            f = 1 / f
+        params = _params_of(integrand)
+        if params:
+            g_param = _flatten(torch.autograd.grad(f, params, x_tot, create_graph=True, retain_graph=True))
+        else:
+            g_param = None
+        g_h = _flatten(torch.autograd.grad(f, h, x_tot))
+    return g_param, g_h.view(int(x.shape[0] / nb_steps), nb_steps, -1).sum(1)
+
+
+def _integrate_grads_chunked(x0, x, integrand, h, nb_steps, grad_output, inv_f):
+    """integrate(compute_grad=True) over batch chunks so the autograd graph stays bounded."""
+    B = x0.shape[0]
+    rows_per_sample = (nb_steps + 1) * max(1, x0.shape[1])
+    chunk = max(1, _TORCH_ROUTE_MAX_ROWS // rows_per_sample)
+    if B <= chunk:
+        return integrate(x0, nb_steps, (x - x0) / nb_steps, integrand, h, True, grad_output, inv_f)
+    g_param_total, g_h_parts = None, []
+    for s in range(0, B, chunk):
+        e = min(B, s + chunk)
+        gp, gh = integrate(x0[s:e], nb_steps, (x[s:e] - x0[s:e]) / nb_steps, integrand, h[s:e], True,
+                           grad_output[s:e], inv_f)
+        if gp is not None:
+            gp = gp.detach()
+            g_param_total = gp if g_param_total is None else g_param_total + gp
+        g_h_parts.append(gh.detach())
+    return g_param_total, torch.cat(g_h_parts, 0)
+
+
+# --------------------------------------------------------------------------------------------------
+# torch route, one node at a time ("sequential", low memory)
+# --------------------------------------------------------------------------------------------------
+def integrate_sequential(x0, nb_steps, step_sizes, integrand, h, compute_grad=False, x_tot=None):
+    w, t = _tables_for(x0, nb_steps)
+    xT = x0 + nb_steps * step_sizes
+    span = xT - x0
+    if compute_grad:
+        g_param, g_h = 0., 0.
+        cot = x_tot * span / 2
+        if not h.requires_grad:
+            h = h.detach().requires_grad_(True)
+        for i in range(nb_steps + 1):
+            xi = x0 + span * (t[i] + 1) / 2
+            dg_param, dg_h = computeIntegrand_sequential(xi, h, integrand, cot)
+            if dg_param is not None:
+                g_param = g_param + w[i] * dg_param
+            g_h = g_h + w[i] * dg_h
+        return (g_param if torch.is_tensor(g_param) else None), g_h
+    z = 0.
+    for i in range(nb_steps + 1):
+        xi = x0 + span * (t[i] + 1) / 2
+        z = z + w[i] * integrand(xi, h)
+    return z * span / 2
+
+
+def computeIntegrand_sequential(x, h, integrand, x_tot):
+    with torch.enable_grad():
+        f = _call(integrand, x, h)
+        params = _params_of(integrand)
+        g_param = (_flatten(torch.autograd.grad(f, params, x_tot, create_graph=True, retain_graph=True))
+                   if params else None)
+        g_h = _flatten(torch.autograd.grad(f, h, x_tot))
+    return g_param, g_h
+
+
+# --------------------------------------------------------------------------------------------------
+# dispatcher
+# --------------------------------------------------------------------------------------------------
+_warned = set()
+
+
+def kernel_route(integrand, x0, x, h, inv_f=False):
+    """The KernelSpec if this call is served by the fused CUDA kernel, else None."""
+    if inv_f or not (torch.is_tensor(x) and x.is_cuda):
+        return None
+    if torch.jit.is_tracing() or torch.jit.is_scripting():
+        return None
+    get_spec = getattr(integrand, "kernel_spec", None)
+    if not callable(get_spec):
+        return None
+    if not (x.dtype == torch.float32 and x0.dtype == torch.float32 and h.dtype == torch.float32):
+        return None
+    spec = get_spec()
+    if spec is None:
+        return None
+    why = spec.supported()
+    if why is not None:
+        key = (type(integrand).__name__, why)
+        if key not in _warned:
+            _warned.add(key)
+            warnings.warn(f"umnn_b200: {type(integrand).__name__} is outside the fused kernel's limits ({why}); "
+                          "using the torch route", RuntimeWarning)
+        return None
+    if not (x0.is_cuda and h.is_cuda and x0.device == x.device and h.device == x.device):
+        raise ValueError("umnn_b200: x0, x and h must live on the same CUDA device")
+    for p in spec.parameters():
+        if p.device != x.device or p.dtype != torch.float32:
+            raise ValueError("umnn_b200: the integrand's parameters must be float32 on the same CUDA device as x")
+    return spec
+
+
+def integral_nograd(x0, x, integrand, h, nb_steps, parallel=True, inv_f=False, cc_weights=None, steps=None):
+    """Integral value only (no autograd graph): kernel route when eligible, else the torch route."""
+    spec = kernel_route(integrand, x0, x, h, inv_f)
+    if spec is not None:
+        return kernel.cc_forward(spec, x0, x, h, nb_steps)[0]
+    if parallel:
+        return integrate(x0, nb_steps, (x - x0) / nb_steps, integrand, h, False, None, inv_f, cc_weights, steps)
+    return integrate_sequential(x0, nb_steps, (x - x0) / nb_steps, integrand, h, False)
+
+
+def _forward_common(ctx, x0, x, integrand, h, nb_steps, inv_f, parallel):
+    spec = kernel_route(integrand, x0, x, h, inv_f)
+    ctx.integrand = integrand
+    ctx.nb_steps = nb_steps
+    ctx.inv_f = inv_f
+    ctx.kernel_spec = spec
+    with torch.no_grad():
+        if spec is not None:
+            need = ctx.needs_input_grad
+            out, fx, fx0 = kernel.cc_forward(spec, x0, x, h, nb_steps, want_fx=bool(need[1]), want_fx0=bool(need[0]))
+            ctx.has_fx, ctx.has_fx0 = fx is not None, fx0 is not None
+            extra = [t for t in (fx, fx0) if t is not None]
+            ctx.save_for_backward(x0.clone(), x.clone(), h, *extra)
+            return out
+        if parallel:
+            out = integrate(x0, nb_steps, (x - x0) / nb_steps, integrand, h, False, inv_f=inv_f)
+        else:
+            out = integrate_sequential(x0, nb_steps, (x - x0) / nb_steps, integrand, h, False)
+        ctx.save_for_backward(x0.clone(), x.clone(), h)
+    return out
+
+
+def _backward_common(ctx, grad_output, parallel):
+    saved = ctx.saved_tensors
+    x0, x, h = saved[0], saved[1], saved[2]
+    integrand, nb_steps, inv_f, spec = ctx.integrand, ctx.nb_steps, ctx.inv_f, ctx.kernel_spec
+    need = ctx.needs_input_grad
+    if spec is not None:
+        grad_output = grad_output.contiguous()
+        extra = list(saved[3:])
+        fx = extra.pop(0) if ctx.has_fx else None
+        fx0 = extra.pop(0) if ctx.has_fx0 else None
+        d_x = fx * grad_output if fx is not None else None
+        d_x0 = -fx0 * grad_output if fx0 is not None else None
+        d_flat = d_h = None
+        if need[3] or need[4]:
+            # parameter / context gradients: torch ops on the same CUDA device, batch-chunked, until
+            # umnn_cc_backward (the fused backward kernel) serves them
+            d_flat, d_h = _integrate_grads_chunked(x0, x, integrand, h, nb_steps, grad_output, False)
+            d_h = d_h.view(h.shape)
+            if not need[3]:
+                d_flat = None
+        return d_x0, d_x, d_flat, d_h
+    # torch route: Leibniz rule for the limits, weighted VJP for parameters and context
+    if parallel:
+        g_param, g_h = _integrate_grads_chunked(x0, x, integrand, h, nb_steps, grad_output, inv_f)
+    else:
+        g_param, g_h = integrate_sequential(x0, nb_steps, (x - x0) / nb_steps, integrand, h, True, grad_output)
+    d_x = integrand(x, h) * grad_output
+    d_x0 = -integrand(x0, h) * grad_output
+    if not need[3]:
+        g_param = None
+    return d_x0, d_x, g_param, g_h.view(h.shape)
+
+
+class ParallelNeuralIntegral(torch.autograd.Function):
+    """apply(x0, x, integrand, flat_params, h, nb_steps=20, inv_f=False) -> integral [B, Dx]."""
+
+    @staticmethod
+    def forward(ctx, x0, x, integrand, flat_params, h, nb_steps=20, inv_f=False):
+        return _forward_common(ctx, x0, x, integrand, h, nb_steps, inv_f, parallel=True)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        d_x0, d_x, d_flat, d_h = _backward_common(ctx, grad_output, parallel=True)
+        return d_x0, d_x, None, d_flat, d_h, None, None
+
+
+class NeuralIntegral(torch.autograd.Function):
+    """apply(x0, x, integrand, flat_params, h, nb_steps=20) -> integral [B, Dx] (node-by-node on the torch route)."""
+
+    @staticmethod
+    def forward(ctx, x0, x, integrand, flat_params, h, nb_steps=20):
+        return _forward_common(ctx, x0, x, integrand, h, nb_steps, False, parallel=False)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        d_x0, d_x, d_flat, d_h = _backward_common(ctx, grad_output, parallel=False)
+        return d_x0, d_x, None, d_flat, d_h, None

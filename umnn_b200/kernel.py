@@ -1,0 +1,128 @@
+"""Torch-tensor front end of the C ABI: packs parameters, builds descriptors, launches on the
+current CUDA stream.  Tensors are passed as raw device pointers; torch is only the allocator and
+the stream provider here.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _native
+from .networks import KernelSpec
+from .quadrature import device_tables
+
+_PRECISION_ENV = {"fp32": _native.PREC_FP32, "bf16x3": _native.PREC_BF16X3, "auto": _native.PREC_AUTO}
+
+
+def default_precision() -> int:
+    """UMNN_B200_PRECISION = fp32 | bf16x3 | auto (default auto)."""
+    return _PRECISION_ENV[os.environ.get("UMNN_B200_PRECISION", "auto").lower()]
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _as_f32c(t: torch.Tensor) -> torch.Tensor:
+    return t if (t.is_contiguous() and t.dtype == torch.float32) else t.contiguous().float()
+
+
+# packed parameters are cached per integrand until a parameter is modified in place (optimizer step,
+# load_state_dict, force_lipschitz all bump `_version`) or replaced (data_ptr changes)
+_pack_cache: Dict[Tuple, Tuple[Tuple, torch.Tensor]] = {}
+
+
+def flat_parameters(spec: KernelSpec) -> torch.Tensor:
+    return torch.cat([p.detach().reshape(-1) for p in spec.parameters()])
+
+
+def packed_parameters(spec: KernelSpec, desc: _native.Desc, device: torch.device) -> torch.Tensor:
+    L = _native.lib()
+    key = (id(spec.linears[0]), desc.precision, str(device))
+    stamp = tuple((p.data_ptr(), p._version) for p in spec.parameters())
+    hit = _pack_cache.get(key)
+    if hit is not None and hit[0] == stamp:
+        return hit[1]
+    nbytes = L.umnn_packed_params_bytes(desc)
+    if nbytes == 0:
+        _native.check(-4 if not L.umnn_last_error() else -4)
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    flat = _as_f32c(flat_parameters(spec))
+    stream = torch.cuda.current_stream(device).cuda_stream
+    with torch.cuda.device(device):
+        _native.check(L.umnn_pack_params(desc, flat.data_ptr(), packed.data_ptr(), stream))
+    if len(_pack_cache) > 64:
+        _pack_cache.clear()
+    _pack_cache[key] = (stamp, packed)
+    return packed
+
+
+def make_desc(spec: KernelSpec, x: torch.Tensor, nb_steps: int, precision: Optional[int] = None) -> _native.Desc:
+    B, Dx = x.shape
+    if spec.layout == _native.LAYOUT_STRIDED_D and Dx != spec.n_dims:
+        raise ValueError(f"x has {Dx} columns but the integrand network was built for {spec.n_dims}")
+    if spec.layout == _native.LAYOUT_CONTIG and Dx != 1:
+        raise ValueError(f"contiguous-context integrands integrate a single variable (x is [B, 1]); got [B, {Dx}]")
+    return _native.make_desc(spec.layout, B, Dx, spec.n_ctx, spec.widths, spec.hidden_act, spec.out_act,
+                             int(nb_steps), default_precision() if precision is None else precision)
+
+
+def cc_forward(spec: KernelSpec, x0: Optional[torch.Tensor], x: torch.Tensor, h: torch.Tensor, nb_steps: int,
+               want_fx: bool = False, want_fx0: bool = False, precision: Optional[int] = None):
+    """One fused launch: (integral, f(x,h) or None, f(x0,h) or None), each [B, Dx].
+
+    Replaces integrate(...) + IntegrandNetwork.forward of the reference (see include/umnn_b200.h).
+    """
+    L = _native.lib()
+    x = _as_f32c(x)
+    h = _as_f32c(h)
+    x0 = None if x0 is None else _as_f32c(x0)
+    desc = make_desc(spec, x, nb_steps, precision)
+    B, Dx = x.shape
+    if h.shape[0] != B or h.shape[1] != spec.n_ctx * Dx:
+        raise ValueError(f"h must be [{B}, {spec.n_ctx * Dx}] for this integrand, got {tuple(h.shape)}")
+    if x0 is not None and x0.shape != x.shape:
+        raise ValueError("x0 and x must have the same shape")
+    dev = x.device
+    out = torch.empty_like(x)
+    fx = torch.empty_like(x) if want_fx else None
+    fx0 = torch.empty_like(x) if want_fx0 else None
+    if B == 0:
+        return out, fx, fx0
+    packed = packed_parameters(spec, desc, dev)
+    w, t = device_tables(nb_steps, dev)
+    ws_bytes = L.umnn_workspace_bytes(desc, 0)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        _native.check(L.umnn_cc_forward(desc, _ptr(x0), x.data_ptr(), h.data_ptr(), packed.data_ptr(),
+                                        t.data_ptr(), w.data_ptr(), out.data_ptr(), _ptr(fx), _ptr(fx0),
+                                        _ptr(ws), ws_bytes, stream))
+    return out, fx, fx0
+
+
+def cc_forward_host(spec_widths, layout, hidden_act, out_act, flat_params, x0, x, h, nb_steps, want_fx=False,
+                    want_fx0=False, device: int = 0, precision: int = _native.PREC_AUTO):
+    """Host-buffer entry (numpy arrays in, numpy arrays out) through umnn_cc_forward_host: the call a
+    non-PyTorch user of the C ABI makes; H2D and D2H copies happen inside."""
+    import numpy as np
+    L = _native.lib()
+    x = np.ascontiguousarray(x, np.float32)
+    h = np.ascontiguousarray(h, np.float32)
+    flat_params = np.ascontiguousarray(flat_params, np.float32)
+    B, Dx = x.shape
+    desc = _native.make_desc(layout, B, Dx, spec_widths[0] - 1, spec_widths, hidden_act, out_act, int(nb_steps),
+                             precision)
+    out = np.empty_like(x)
+    fx = np.empty_like(x) if want_fx else None
+    fx0 = np.empty_like(x) if want_fx0 else None
+    x0p = None
+    if x0 is not None:
+        x0 = np.ascontiguousarray(x0, np.float32)
+        x0p = x0.ctypes.data
+    _native.check(L.umnn_cc_forward_host(desc, x0p, x.ctypes.data, h.ctypes.data, flat_params.ctypes.data,
+                                         out.ctypes.data, None if fx is None else fx.ctypes.data,
+                                         None if fx0 is None else fx0.ctypes.data, device))
+    return out, fx, fx0
