@@ -1,0 +1,72 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol include/umnn_b200.h declares,
+validates descriptors, and its host-only entry points work without a GPU (no compute calls here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_DIR, REPO
+from umnn_b200 import _native, build as native_build
+
+
+@pytest.fixture(scope="module")
+def lib():
+    native_build.build()
+    return _native.lib()
+
+
+def test_exports_every_declared_symbol(lib):
+    header = open(os.path.join(REPO, "include", "umnn_b200.h")).read()
+    declared = set(re.findall(r"UMNN_API\s+[\w\s\*]+?\b(umnn_\w+)\s*\(", header))
+    assert declared == set(_native.EXPORTS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.umnn_abi_version() == _native.UMNN_ABI_VERSION
+
+
+def test_desc_struct_matches_header_layout():
+    # int32 abi, int32 layout, int64 n_samples, 3 x int32, int32[9], 4 x int32  -> 80 bytes
+    assert ctypes.sizeof(_native.Desc) == 80
+    assert _native.Desc.n_samples.offset == 8 and _native.Desc.widths.offset == 28
+
+
+def test_cc_tables_match_reference_bitwise(lib):
+    g = np.load(os.path.join(GOLDEN_DIR, "cc_weights.npz"))
+    for Q in (1, 2, 5, 20, 30, 50, 100, 200):
+        t = np.zeros(Q + 1, np.float32)
+        w = np.zeros(Q + 1, np.float32)
+        assert lib.umnn_cc_tables(Q, t.ctypes.data, w.ctypes.data) == 0
+        np.testing.assert_array_equal(t, g[f"t_{Q}"])
+        assert np.max(np.abs(w - g[f"w_{Q}"])) <= np.spacing(np.float32(np.max(np.abs(w))))
+    assert lib.umnn_cc_tables(0, t.ctypes.data, w.ctypes.data) == -2
+    assert b"nb_steps" in lib.umnn_last_error()
+
+
+def test_descriptor_validation_and_sizes(lib):
+    d = _native.make_desc(_native.LAYOUT_STRIDED_D, 10, 6, 30, [31, 200, 200, 200, 1], _native.ACT_LEAKY_RELU,
+                          _native.OUT_ELU_PLUS_1, 50, _native.PREC_FP32)
+    assert lib.umnn_param_count(d) == 31 * 200 + 200 + 2 * (200 * 200 + 200) + 200 + 1 == 87001
+    assert lib.umnn_packed_params_bytes(d) >= 87001 * 4
+    bad = _native.make_desc(_native.LAYOUT_CONTIG, 10, 6, 30, [31, 200, 1], 0, 0, 50)
+    assert lib.umnn_param_count(bad) == -1 and b"CONTIG" in lib.umnn_last_error()
+    bad = _native.make_desc(_native.LAYOUT_STRIDED_D, 10, 6, 30, [30, 200, 1], 0, 0, 50)
+    assert lib.umnn_packed_params_bytes(bad) == 0 and b"widths[0]" in lib.umnn_last_error()
+    bad = _native.make_desc(_native.LAYOUT_STRIDED_D, 10, 6, 30, [31, 300, 1], 0, 0, 50)
+    assert lib.umnn_param_count(bad) == -1
+    bad = _native.make_desc(_native.LAYOUT_STRIDED_D, 10, 6, 30, [31, 200, 1], 0, 0, 50)
+    bad.abi_version = 99
+    assert lib.umnn_param_count(bad) == -1 and b"abi_version" in lib.umnn_last_error()
+    with pytest.raises(_native.NativeError):
+        _native.check(lib.umnn_pack_params(d, None, None, None))
+    # zero samples is a valid no-op even without a device
+    d0 = _native.make_desc(_native.LAYOUT_STRIDED_D, 0, 6, 30, [31, 200, 1], 1, 0, 50)
+    assert lib.umnn_cc_forward(d0, None, None, None, None, None, None, None, None, None, None, 0, None) == 0
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_native, "_lib", None)
+    monkeypatch.setattr(_native, "LIB_PATH", os.path.join(tmp_path, "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU/eager fallback"):
+        _native.lib()

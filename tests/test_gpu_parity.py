@@ -1,0 +1,297 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle and the golden
+vectors recorded from the reference.  Run on the B200 box with `pytest -m gpu`.
+
+Tolerances (float32 path): integral max rel-err <= 1e-5 (north star; the FP32 kernel is expected
+near 5e-7, the noise floor between two fp32 summation orders); point evaluations within
+1e-5 relative + two ELU+1 quanta (2^-23) absolute; gradients <= 1e-3 rel-to-max (fp32 vs
+fp64 reference gradients already differ by 1.2e-4 because of LeakyReLU kink flips).
+"""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_CASES, GOLDEN_DIR, load_golden_case, rel_err, rel_to_max
+from oracle import c_binding, umnn_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+INTEGRAL_TOL = 1e-5
+GRAD_TOL = 1e-3
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _point_ok(got, want):
+    return np.all(np.abs(got - want) <= 1e-5 * np.abs(want) + 2.4e-7)
+
+
+def _net_for(spec, flat, layout, Dx):
+    from umnn_b200 import IntegrandNN, IntegrandNetwork
+    hidden = list(spec.widths[1:-1])
+    if layout == "strided":
+        net = IntegrandNetwork(Dx, spec.widths[0], hidden, 1,
+                               act_func="ELU" if spec.out_act == orc.OUT_ELU_PLUS_1 else "Sigmoid")
+    else:
+        net = IntegrandNN(spec.widths[0], hidden)
+    off = 0
+    with torch.no_grad():
+        for p in net.parameters():
+            p.copy_(torch.from_numpy(flat[off:off + p.numel()].copy()).view_as(p))
+            off += p.numel()
+    return net.to(_dev())
+
+
+def _run_kernel(spec, flat, x0, x, h, Q, layout, want_f=True, x0_none=False):
+    from umnn_b200 import cc_integrate
+    net = _net_for(spec, flat, layout, x.shape[1])
+    d = _dev()
+    out, fx, fx0 = cc_integrate(net, None if x0_none else torch.from_numpy(x0).to(d), torch.from_numpy(x).to(d),
+                                torch.from_numpy(h).to(d), Q, want_fx=want_f, want_fx0=want_f)
+    torch.cuda.synchronize()
+    return out.cpu().numpy(), None if fx is None else fx.cpu().numpy(), None if fx0 is None else fx0.cpu().numpy()
+
+
+def test_native_library_is_the_loaded_path():
+    from umnn_b200 import _native
+    lib = _native.lib()
+    assert lib.umnn_abi_version() == 1
+    loaded = open("/proc/self/maps").read()
+    assert "libumnn_b200.so" in loaded
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_forward_matches_golden_and_oracle(name):
+    spec, flat, inp, g = load_golden_case(name)
+    out, fx, fx0 = _run_kernel(spec, flat, inp["x0"], inp["x"], inp["h"], inp["Q"], inp["layout"])
+    assert rel_err(out, g["par_integral"]) < INTEGRAL_TOL
+    assert rel_err(out, g["fp64_integral"].astype(np.float32)) < INTEGRAL_TOL
+    ref = orc.integrate_parallel(spec, flat, inp["x0"], inp["x"], inp["h"], inp["Q"], inp["layout"])
+    assert rel_err(out, ref) < INTEGRAL_TOL
+    assert _point_ok(fx, g["f_at_x"]) and _point_ok(fx0, g["f_at_x0"])
+    # integral only (no extra rows) gives the same integral bit for bit or within summation noise
+    out2, _, _ = _run_kernel(spec, flat, inp["x0"], inp["x"], inp["h"], inp["Q"], inp["layout"], want_f=False)
+    assert rel_err(out2, out) < 2e-6
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("fn_name", ["ParallelNeuralIntegral", "NeuralIntegral"])
+def test_autograd_function_on_cuda_matches_golden(name, fn_name):
+    import umnn_b200
+    spec, flat, inp, g = load_golden_case(name)
+    fn = getattr(umnn_b200, fn_name)
+    net = _net_for(spec, flat, inp["layout"], inp["Dx"])
+    d = _dev()
+    x0 = torch.from_numpy(inp["x0"]).to(d).requires_grad_(True)
+    x = torch.from_numpy(inp["x"]).to(d).requires_grad_(True)
+    h = torch.from_numpy(inp["h"]).to(d).requires_grad_(True)
+    z = fn.apply(x0, x, net, torch.cat([p.view(-1) for p in net.parameters()]), h, inp["Q"])
+    z.backward(torch.from_numpy(inp["grad_out"]).to(d))
+    assert rel_err(z.detach().cpu().numpy(), g["par_integral"]) < INTEGRAL_TOL
+    assert rel_to_max(x.grad.cpu().numpy(), g["par_dx"]) < 1e-5
+    assert rel_to_max(x0.grad.cpu().numpy(), g["par_dx0"]) < 1e-5
+    assert rel_to_max(h.grad.cpu().numpy(), g["par_dh"]) < GRAD_TOL
+    dflat = torch.cat([p.grad.view(-1) for p in net.parameters()]).cpu().numpy()
+    assert rel_to_max(dflat[::int(g["meta_dflat_stride"])], g["par_dflat"]) < GRAD_TOL
+
+
+@pytest.mark.parametrize("Q", [1, 2, 3, 7, 31, 127, 128, 200, 1024])
+def test_node_count_edges(Q):
+    """Q+1(+2) rows per slot below, at and above the 128-row tile; slots straddle tiles."""
+    spec = orc.MLPSpec((4, 24, 16, 1))
+    flat = orc.synth_params(spec, Q, 2.0)
+    x0, x, h, _ = orc.synth_inputs(13, 5, 15, Q + 1, x0_zero=False)
+    out, fx, fx0 = _run_kernel(spec, flat, x0, x, h, Q, "strided")
+    ref, rfx, rfx0 = c_binding.cc_forward(spec, flat, x0, x, h, Q)
+    assert rel_err(out, ref) < INTEGRAL_TOL
+    assert _point_ok(fx, rfx) and _point_ok(fx0, rfx0)
+
+
+@pytest.mark.parametrize("hidden", [[8], [20, 20], [50, 50, 50, 50], [64, 64, 64], [100, 50, 50, 50, 50],
+                                    [256, 256], [17, 33, 65], [12] * 7])
+@pytest.mark.parametrize("acts", [(orc.HIDDEN_LEAKY, orc.OUT_ELU_PLUS_1), (orc.HIDDEN_LEAKY, orc.OUT_SIGMOID)])
+def test_network_shapes_strided(hidden, acts):
+    E, D, B, Q = 6, 7, 19, 20
+    spec = orc.MLPSpec(tuple([1 + E] + hidden + [1]), acts[0], acts[1])
+    flat = orc.synth_params(spec, len(hidden), 1.7)
+    x0, x, h, _ = orc.synth_inputs(B, D, E * D, 3, x0_zero=False)
+    out, fx, fx0 = _run_kernel(spec, flat, x0, x, h, Q, "strided")
+    ref, rfx, rfx0 = c_binding.cc_forward(spec, flat, x0, x, h, Q)
+    assert rel_err(out, ref) < INTEGRAL_TOL
+    assert _point_ok(fx, rfx) and _point_ok(fx0, rfx0)
+
+
+@pytest.mark.parametrize("E", [0, 1, 2, 30, 255])
+def test_contiguous_layout_and_context_sizes(E):
+    spec = orc.MLPSpec((1 + E, 32, 32, 1), orc.HIDDEN_RELU, orc.OUT_ELU_PLUS_1)
+    flat = orc.synth_params(spec, E, 1.5)
+    x0, x, h, _ = orc.synth_inputs(41, 1, E, 5, x0_zero=False)
+    out, fx, fx0 = _run_kernel(spec, flat, x0, x, h, 25, "contig")
+    ref, rfx, rfx0 = c_binding.cc_forward(spec, flat, x0, x, h, 25, layout="contig")
+    assert rel_err(out, ref) < INTEGRAL_TOL
+    assert _point_ok(fx, rfx) and _point_ok(fx0, rfx0)
+
+
+def test_batch_edges_and_null_x0():
+    spec = orc.MLPSpec((3, 16, 1))
+    flat = orc.synth_params(spec, 0, 1.0)
+    for B in (0, 1, 2, 129, 1000):
+        x0, x, h, _ = orc.synth_inputs(B, 2, 4, B, x0_zero=True)
+        out, fx, _ = _run_kernel(spec, flat, x0, x, h, 10, "strided", x0_none=True)
+        assert out.shape == (B, 2)
+        if B:
+            ref, rfx, _ = c_binding.cc_forward(spec, flat, x0, x, h, 10)
+            assert rel_err(out, ref) < INTEGRAL_TOL and _point_ok(fx, rfx)
+
+
+def test_degenerate_limits_and_antisymmetry():
+    spec = orc.MLPSpec((31, 200, 200, 200, 1))
+    flat = orc.synth_params(spec, 0, 2.0)
+    x0, x, h, _ = orc.synth_inputs(64, 6, 180, 2, x0_zero=False)
+    same, _, _ = _run_kernel(spec, flat, x, x, h, 50, "strided", want_f=False)
+    assert np.all(same == 0.0)
+    fwd, _, _ = _run_kernel(spec, flat, x0, x, h, 50, "strided", want_f=False)
+    bwd, _, _ = _run_kernel(spec, flat, x, x0, h, 50, "strided", want_f=False)
+    assert rel_err(-bwd, fwd, floor=1e-4) < 1e-5
+
+
+def test_deterministic_and_batch_invariant():
+    spec = orc.MLPSpec((31, 200, 200, 200, 1))
+    flat = orc.synth_params(spec, 0, 1.0)
+    x0, x, h, _ = orc.synth_inputs(300, 6, 180, 2, x0_zero=False)
+    a, _, _ = _run_kernel(spec, flat, x0, x, h, 50, "strided")
+    b, _, _ = _run_kernel(spec, flat, x0, x, h, 50, "strided")
+    np.testing.assert_array_equal(a, b)
+    c, _, _ = _run_kernel(spec, flat, x0[100:200], x[100:200], h[100:200], 50, "strided")
+    assert rel_err(c, a[100:200]) < 2e-6
+
+
+def test_host_buffer_entry():
+    from umnn_b200 import _native, kernel
+    spec = orc.MLPSpec((11, 100, 100, 100, 100, 1))
+    flat = orc.synth_params(spec, 0, 1.0)
+    x0, x, h, _ = orc.synth_inputs(50, 2, 20, 1, x0_zero=False)
+    out, fx, fx0 = kernel.cc_forward_host(spec.widths, _native.LAYOUT_STRIDED_D, _native.ACT_LEAKY_RELU,
+                                          _native.OUT_ELU_PLUS_1, flat, x0, x, h, 50, True, True)
+    ref, rfx, rfx0 = c_binding.cc_forward(spec, flat, x0, x, h, 50)
+    assert rel_err(out, ref) < INTEGRAL_TOL and _point_ok(fx, rfx) and _point_ok(fx0, rfx0)
+
+
+def test_native_errors_surface_as_exceptions():
+    from umnn_b200 import IntegrandNetwork, cc_integrate
+    net = IntegrandNetwork(3, 3, [16], 1).to(_dev())
+    x = torch.randn(4, 3, device=_dev())
+    with pytest.raises(ValueError):
+        cc_integrate(net, None, x, torch.randn(4, 5, device=_dev()), 10)           # wrong h width
+    with pytest.raises(ValueError):
+        cc_integrate(net, None, x.cpu(), torch.randn(4, 6), 10)                    # CPU tensors
+    from umnn_b200 import _native
+    with pytest.raises(_native.NativeError):
+        cc_integrate(net, None, x, torch.randn(4, 6, device=_dev()), 5000)         # Q out of range
+
+
+# ---- full-size configurations (BASELINE.json): sampled oracle checks + size-independent properties ----
+def _full_size_check(B, D, E, hidden, Q, n_check, seed):
+    from umnn_b200 import IntegrandNetwork, cc_integrate
+    spec = orc.MLPSpec(tuple([1 + E] + hidden + [1]))
+    flat = orc.synth_params(spec, 0, 1.0)
+    net = _net_for(spec, flat, "strided", D)
+    d = _dev()
+    g = torch.Generator(device=d).manual_seed(seed)
+    x = 2 * torch.randn(B, D, device=d, generator=g)
+    h = torch.randn(B, E * D, device=d, generator=g)
+    out, fx, _ = cc_integrate(net, None, x, h, Q, want_fx=True)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all() and torch.isfinite(fx).all() and (fx >= 0).all()
+    # (1) a random subset of samples against the C oracle
+    idx = torch.randperm(B, generator=torch.Generator().manual_seed(seed))[:n_check]
+    xs, hs = x[idx.to(d)].cpu().numpy(), h[idx.to(d)].cpu().numpy()
+    ref, rfx, _ = c_binding.cc_forward(spec, flat, np.zeros_like(xs), xs, hs, Q)
+    assert rel_err(out[idx.to(d)].cpu().numpy(), ref) < INTEGRAL_TOL
+    assert _point_ok(fx[idx.to(d)].cpu().numpy(), rfx)
+    # (2) checksum of checksums: the same samples recomputed in 7 uneven chunks give the same totals
+    bounds = [0] + sorted(np.random.RandomState(seed).choice(np.arange(1, B), 6, replace=False).tolist()) + [B]
+    total = 0.0
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        part, _, _ = cc_integrate(net, None, x[a:b], h[a:b], Q, want_fx=True)
+        total += float(part.double().sum())
+        assert rel_err(part.cpu().numpy(), out[a:b].cpu().numpy()) < 2e-6
+    assert abs(total - float(out.double().sum())) < 1e-6 * float(out.double().abs().sum())
+    # (3) sign: f > 0 so the integral from 0 has the sign of x
+    assert torch.all((out * x) >= 0)
+
+
+def test_config3_full_size():
+    _full_size_check(10000, 6, 30, [200, 200, 200], 50, n_check=64, seed=3)
+
+
+def test_config2_full_size():
+    _full_size_check(10000, 2, 10, [100, 100, 100, 100], 50, n_check=256, seed=2)
+
+
+def test_config5_full_size():
+    _full_size_check(100, 784, 30, [100, 50, 50, 50, 50], 50, n_check=4, seed=5)
+
+
+def test_config4_full_size():
+    _full_size_check(65536, 63, 30, [200, 200, 200], 100, n_check=4, seed=4)
+
+
+# ---- flows and the monotone regressor on the device ----------------------------------------------------
+def _flow_from_golden(device):
+    from umnn_b200 import UMNNMAFFlow
+    g = dict(np.load(os.path.join(GOLDEN_DIR, "flow_ll.npz"), allow_pickle=False))
+    D, E, Q, B = (int(v) for v in g["meta"])
+    model = UMNNMAFFlow(nb_flow=2, nb_in=D, hidden_derivative=[50, 50], hidden_embedding=[64, 64],
+                        embedding_s=E, nb_steps=Q, solver="CCParallel")
+    sd = model.state_dict()
+    rng = np.random.RandomState(11)
+    for k, v in sd.items():
+        if k.endswith(".weight") or k.endswith(".bias"):
+            fan_in = v.shape[1] if v.dim() == 2 else sd[k.replace(".bias", ".weight")].shape[1]
+            sd[k] = torch.from_numpy(rng.uniform(-1, 1, size=tuple(v.shape)).astype(np.float32) * (1.5 / np.sqrt(fan_in)))
+    model.load_state_dict(sd)
+    x = rng.standard_normal((B, D)).astype(np.float32)
+    return model.to(device), x, g
+
+
+def test_flow_compute_ll_on_cuda_matches_reference():
+    model, xn, g = _flow_from_golden(_dev())
+    x = torch.from_numpy(xn).to(_dev()).requires_grad_(True)
+    ll, z = model.compute_ll(x)
+    ll.sum().backward()
+    assert np.max(np.abs(ll.detach().cpu().numpy() - g["ll"])) < 2e-5 * np.max(np.abs(g["ll"]))
+    assert np.max(np.abs(z.detach().cpu().numpy() - g["z"])) < 2e-5 * max(1.0, np.max(np.abs(g["z"])))
+    assert rel_to_max(x.grad.cpu().numpy(), g["dx"]) < GRAD_TOL
+    for k, p in model.named_parameters():
+        if p.grad is not None:
+            assert rel_to_max(p.grad.cpu().numpy(), g["grad/" + k]) < 2e-3, k
+    model.eval()
+    with torch.no_grad():
+        z_eval = model.forward(torch.from_numpy(xn).to(_dev()))
+        with contextlib.redirect_stdout(io.StringIO()):
+            x_back = model.invert(torch.from_numpy(g["z"][:4].copy()).to(_dev()), iter=5)
+    assert np.max(np.abs(z_eval.cpu().numpy() - g["z_forward_eval"])) < 2e-5 * max(1.0, np.max(np.abs(g["z_forward_eval"])))
+    assert np.max(np.abs(x_back.cpu().numpy() - g["invert_x"])) < 1e-3
+
+
+def test_monotonic_nn_on_cuda():
+    from umnn_b200 import MonotonicNN
+    torch.manual_seed(0)
+    model = MonotonicNN(3, [64, 64, 64], nb_steps=50, dev=_dev()).to(_dev())
+    x = torch.randn(100, 1, device=_dev())
+    h = torch.randn(100, 2, device=_dev())
+    y = model(x, h)
+    y.sum().backward()
+    cpu = MonotonicNN(3, [64, 64, 64], nb_steps=50)
+    cpu.load_state_dict({k: v.cpu() for k, v in model.state_dict().items()})
+    y_cpu = cpu(x.cpu(), h.cpu())
+    assert torch.allclose(y.detach().cpu(), y_cpu.detach(), rtol=1e-5, atol=1e-5)
+    xs = torch.linspace(-3, 3, 200, device=_dev()).view(-1, 1)
+    ys = model(xs, h[:1].expand(200, -1)).view(-1)
+    assert torch.all(ys[1:] >= ys[:-1] - 1e-5)

@@ -283,3 +283,22 @@ class NeuralIntegral(torch.autograd.Function):
     def backward(ctx, grad_output):
         d_x0, d_x, d_flat, d_h = _backward_common(ctx, grad_output, parallel=False)
         return d_x0, d_x, None, d_flat, d_h, None
+
+
+def cc_integrate(integrand, x0, x, h, nb_steps, want_fx=False, want_fx0=False):
+    """Functional, value-only entry of the fused kernel: (integral, f(x,h) | None, f(x0,h) | None).
+
+    One launch gives the integral of UMNNMAF.forward (UMNNMAF.py:76-134) and the Jacobian point of
+    UMNNMAF.compute_log_jac (:136-139).  CUDA float32 tensors and a recognised integrand are
+    required -- this entry never takes the torch route.
+    """
+    if x0 is None:
+        x0_probe = x
+    else:
+        x0_probe = x0
+    spec = kernel_route(integrand, x0_probe, x, h, False)
+    if spec is None:
+        raise ValueError("cc_integrate needs CUDA float32 tensors and a recognised integrand "
+                         "(IntegrandNetwork, IntegrandNN, ContiguousIntegrand) within the kernel's limits")
+    with torch.no_grad():
+        return kernel.cc_forward(spec, x0, x, h, nb_steps, want_fx=want_fx, want_fx0=want_fx0)
