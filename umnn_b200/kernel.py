@@ -5,7 +5,7 @@ the stream provider here.
 from __future__ import annotations
 
 import os
-from typing import Dict, Optional, Tuple
+from typing import Optional
 
 import torch
 
@@ -29,34 +29,43 @@ def _as_f32c(t: torch.Tensor) -> torch.Tensor:
     return t if (t.is_contiguous() and t.dtype == torch.float32) else t.contiguous().float()
 
 
-# packed parameters are cached per integrand until a parameter is modified in place (optimizer step,
-# load_state_dict, force_lipschitz all bump `_version`) or replaced (data_ptr changes)
-_pack_cache: Dict[Tuple, Tuple[Tuple, torch.Tensor]] = {}
-
-
 def flat_parameters(spec: KernelSpec) -> torch.Tensor:
     return torch.cat([p.detach().reshape(-1) for p in spec.parameters()])
 
 
 def packed_parameters(spec: KernelSpec, desc: _native.Desc, device: torch.device) -> torch.Tensor:
+    """Device-side packed parameter block for this launch.
+
+    Re-packed on every call (two tiny launches) while the integrand is in training mode.  In eval
+    mode the block is cached ON the first Linear module (so it dies with the network) and reused
+    while every parameter keeps its storage address and autograd version -- in-place updates
+    (optimizer steps, load_state_dict, force_lipschitz) bump the version and invalidate it.
+    """
     L = _native.lib()
-    key = (id(spec.linears[0]), desc.precision, str(device))
-    stamp = tuple((p.data_ptr(), p._version) for p in spec.parameters())
-    hit = _pack_cache.get(key)
-    if hit is not None and hit[0] == stamp:
-        return hit[1]
+    owner = spec.linears[0]
+    stamp = None
+    if not owner.training:
+        stamp = (desc.precision, str(device)) + tuple((id(p), p.data_ptr(), p._version) for p in spec.parameters())
+        hit = owner.__dict__.get("_umnn_packed")
+        if hit is not None and hit[0] == stamp:
+            return hit[1]
     nbytes = L.umnn_packed_params_bytes(desc)
     if nbytes == 0:
-        _native.check(-4 if not L.umnn_last_error() else -4)
+        msg = L.umnn_last_error()
+        raise _native.NativeError(_native_err_unsupported, msg.decode("utf-8", "replace") if msg else "")
     packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
     flat = _as_f32c(flat_parameters(spec))
     stream = torch.cuda.current_stream(device).cuda_stream
     with torch.cuda.device(device):
         _native.check(L.umnn_pack_params(desc, flat.data_ptr(), packed.data_ptr(), stream))
-    if len(_pack_cache) > 64:
-        _pack_cache.clear()
-    _pack_cache[key] = (stamp, packed)
+    if stamp is not None:
+        owner.__dict__["_umnn_packed"] = (stamp, packed)
+    else:
+        owner.__dict__.pop("_umnn_packed", None)
     return packed
+
+
+_native_err_unsupported = -4
 
 
 def make_desc(spec: KernelSpec, x: torch.Tensor, nb_steps: int, precision: Optional[int] = None) -> _native.Desc:
