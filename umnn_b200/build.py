@@ -10,8 +10,8 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libumnn_b200.so")
-SOURCES = ["umnn_abi.cu", "cc_forward_fp32.cu"]
-HEADERS = ["umnn_common.cuh", os.path.join("..", "..", "include", "umnn_b200.h")]
+SOURCES = ["umnn_abi.cu", "cc_forward_fp32.cu", "cc_forward_tc.cu"]
+HEADERS = ["umnn_common.cuh", "tc_common.cuh", "tc_layout.cuh", os.path.join("..", "..", "include", "umnn_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC,-fvisibility=hidden", "--use_fast_math=false"]
 
@@ -36,6 +36,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB_PATH
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    if os.environ.get("UMNN_B200_TC_DEBUG"):
+        # bounded mbarrier spins: a protocol bug traps with a message instead of hanging the GPU
+        flags += ["-DUMNN_TC_SPIN_LIMIT=" + os.environ.get("UMNN_B200_TC_SPIN_LIMIT", "400000000LL")]
     cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + \
           [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH]
     res = subprocess.run(cmd, capture_output=True, text=True)

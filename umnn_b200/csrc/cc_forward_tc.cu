@@ -1,0 +1,575 @@
+// Fused Clenshaw-Curtis forward, BF16x3 tensor-core path (UMNN_PREC_BF16X3) for sm_100a.
+//
+// One persistent CTA PAIR (cluster of 2, tcgen05 cta_group::2) per two SMs.  Every CTA owns a contiguous
+// range of whole slots and walks its (slot, node) rows in tiles of 128; the pair runs in lock-step so
+// one elected thread of the leader CTA issues every MMA for both (M = 256).
+//
+//   weights      all hidden-to-hidden matrices, split into bf16 hi + lo, live in SHARED MEMORY for the
+//                whole kernel (each CTA holds half of the N rows of every matrix; cta_group::2 reads
+//                both halves), staged once per CTA by a bulk-TMA copy.
+//   activations  live in TENSOR MEMORY only: region P = columns [0,256), Q = [256,512).  An MMA layer
+//                reads its A operand (bf16 hi/lo pairs) from one region and accumulates fp32 into the
+//                other; the epilogue converts the accumulator IN PLACE into the next layer's A operand
+//                (16 fp32 columns -> 8 hi + 8 lo packed columns), chunk by chunk, and the next layer's
+//                K-block MMAs start as soon as their chunk is converted.
+//   per K block  D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo      (fp32-class products)
+//   layer 1      rank-1 on CUDA cores: act(x_node * w1x + c_slot), c_slot = b1 + W1h.h_slot once per slot
+//   output layer dot product on CUDA cores while the last accumulator is read, ELU+1, CC weight,
+//                deterministic segmented sum per slot, (z*(xT-x0))/2.
+//
+// Warp roles per CTA (384 threads): warps 0-7 epilogue (TMEM lane quadrant = warp%4, even/odd 16-column
+// chunks = warp/4), warps 8-10 "prep" (abscissae + c_slot for the tile two ahead), warp 11 MMA issuer.
+#include "tc_common.cuh"
+#include "tc_layout.cuh"
+
+#include <stdlib.h>
+
+namespace umnn {
+
+namespace {
+
+using namespace tc;
+
+constexpr int kEpiWarps = 8;
+constexpr int kPrepWarps = 3;
+constexpr int kMmaWarp = kEpiWarps + kPrepWarps;
+constexpr int kThreads = (kMmaWarp + 1) * 32;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kPrepThreads = kPrepWarps * 32;
+constexpr uint32_t kColP = 0, kColQ = kTcRegionCols;
+
+// barrier indices
+constexpr int BAR_READY = 0;                                   // [layer][16]
+constexpr int BAR_ACC = BAR_READY + kTcMaxMmaLayers * 16;      // [layer][2]
+constexpr int BAR_PREP_FULL = BAR_ACC + kTcMaxMmaLayers * 2;   // [kTcPrepBufs]
+constexpr int BAR_PREP_EMPTY = BAR_PREP_FULL + kTcPrepBufs;    // [kTcPrepBufs]
+constexpr int BAR_WLOAD = BAR_PREP_EMPTY + kTcPrepBufs;
+constexpr int BAR_PEER = BAR_WLOAD + 1;
+constexpr int BAR_COUNT = BAR_PEER + 1;
+static_assert(BAR_COUNT <= kTcNumBars, "barrier table too small");
+
+struct TcParams {
+    const float* x0;
+    const float* x;
+    const float* h;
+    const float* nodes;
+    const float* weights;
+    const uint8_t* blobs;  // [2][blob_bytes]
+    float* out;
+    float* out_fx;
+    float* out_fx0;
+    long long n_slots;
+    long long slots_per_cta;
+    int tiles_per_cta;
+    int D, E, layout, Q, rps, out_act;
+    TcLayout L;
+    TcSmem S;
+};
+
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"r"(kEpiThreads) : "memory"); }
+
+__device__ __forceinline__ const float* slot_ctx(const TcParams& p, long long slot, int* stride) {
+    if (p.layout == UMNN_LAYOUT_STRIDED_D) {
+        const long long n = slot / p.D;
+        const int d = (int)(slot - n * p.D);
+        *stride = p.D;
+        return p.h + n * (long long)p.E * p.D + d;
+    }
+    *stride = 1;
+    return p.h + slot * (long long)p.E;
+}
+
+template <int HIDDEN_ACT>
+__device__ __forceinline__ float hact(float v) {
+    return HIDDEN_ACT == UMNN_ACT_LEAKY_RELU ? fmaxf(v, v * kLeakySlope) : fmaxf(v, 0.0f);
+}
+
+template <int HIDDEN_ACT>
+__global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const TcLayout& L = p.L;
+    const int T = p.tiles_per_cta;
+
+    float* cvec = reinterpret_cast<float*>(smem + p.S.off_cvec);      // [bufs][max_slots][npad1]
+    float* xnode = reinterpret_cast<float*>(smem + p.S.off_xnode);    // [bufs][128]
+    int* lsrel = reinterpret_cast<int*>(smem + p.S.off_lsrel);        // [bufs][128]
+    int* nodeid = reinterpret_cast<int*>(smem + p.S.off_node);        // [bufs][128]
+    float* part = reinterpret_cast<float*>(smem + p.S.off_part);      // [128]
+    float* fval = reinterpret_cast<float*>(smem + p.S.off_fval);      // [128]
+    float* tab_t = reinterpret_cast<float*>(smem + p.S.off_tabt);
+    float* tab_w = reinterpret_cast<float*>(smem + p.S.off_tabw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.S.off_bars);
+    uint32_t* holder = reinterpret_cast<uint32_t*>(smem + p.S.off_holder);
+    const float* w1x = reinterpret_cast<const float*>(smem + L.off_w1x);
+    const float* b1p = reinterpret_cast<const float*>(smem + L.off_b1p);
+    const float* w1h = reinterpret_cast<const float*>(smem + L.off_w1h);
+    const float* w4 = reinterpret_cast<const float*>(smem + L.off_w4);
+
+    const long long slot_begin = (long long)blockIdx.x * p.slots_per_cta;
+    long long slot_end = slot_begin + p.slots_per_cta;
+    if (slot_end > p.n_slots) slot_end = p.n_slots;
+    const long long n_rows = slot_end > slot_begin ? (slot_end - slot_begin) * p.rps : 0;
+
+    // ---------------------------------------------------------------- setup
+    if (tid == 0) {
+        for (int m = 0; m < kTcMaxMmaLayers; ++m) {
+            for (int j = 0; j < 16; ++j) mbar_init(&bars[BAR_READY + m * 16 + j], 8);   // 4 warps x 2 CTAs
+            for (int s = 0; s < 2; ++s) mbar_init(&bars[BAR_ACC + m * 2 + s], 1);       // tcgen05.commit
+        }
+        for (int b = 0; b < kTcPrepBufs; ++b) {
+            mbar_init(&bars[BAR_PREP_FULL + b], kPrepWarps);
+            mbar_init(&bars[BAR_PREP_EMPTY + b], kEpiWarps);
+        }
+        mbar_init(&bars[BAR_WLOAD], 1);
+        mbar_init(&bars[BAR_PEER], 2);
+        fence_mbar_init();
+    }
+    if (warp == kMmaWarp) tmem_alloc<2>(holder, 512);
+    for (int i = tid; i <= p.Q; i += kThreads) {
+        tab_t[i] = p.nodes[i];
+        tab_w[i] = p.weights[i];
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after_sync();
+    const uint32_t tbase = *holder;
+
+    if (warp == kMmaWarp) {
+        // =========================================================== MMA issuer warp
+        if (lane == 0) {
+            // stage this CTA's parameter blob with bulk-TMA copies (<= 32 KB each) on one mbarrier
+            mbar_expect_tx(&bars[BAR_WLOAD], L.blob_bytes);
+            const uint8_t* src = p.blobs + (size_t)rank * L.blob_bytes;
+            for (uint32_t off = 0; off < L.blob_bytes; off += 32768u) {
+                const uint32_t n = (L.blob_bytes - off < 32768u) ? (L.blob_bytes - off) : 32768u;
+                bulk_g2s(smem + off, src + off, n, &bars[BAR_WLOAD]);
+            }
+            mbar_wait(&bars[BAR_WLOAD], 0, 100);
+            mbar_arrive_cluster(&bars[BAR_PEER], 0);    // tell the leader this CTA's half of B is resident
+            if (rank == 0) {
+                mbar_wait_cluster(&bars[BAR_PEER], 0, 101);
+                const uint32_t sbase = smem_u32(smem);
+                for (int t = 0; t < T; ++t) {
+                    const uint32_t par = (uint32_t)(t & 1);
+                    for (int m = 0; m < L.n_mma; ++m) {
+                        const TcMmaLayer& y = L.layer[m];
+                        const uint32_t col_a = (m & 1) ? kColP : kColQ;   // A operand region
+                        const uint32_t col_d = (m & 1) ? kColQ : kColP;   // accumulator region
+                        const int n_kb = y.kpad / 16;
+                        for (int s = 0; s < y.nseg; ++s) {
+                            const uint32_t idesc = make_idesc_bf16_f32(256, y.seg_n[s]);
+                            const uint32_t lbo = (uint32_t)(y.seg_n[s] / 16) * 128u;
+                            const uint32_t blk = 2u * lbo;
+                            const uint32_t d_addr = tbase + col_d + (uint32_t)y.seg_begin[s];
+                            for (int kb = 0; kb < n_kb; ++kb) {
+                                if (s == 0) {
+                                    mbar_wait_cluster(&bars[BAR_READY + m * 16 + kb], par, 200 + m * 16 + kb);
+                                    tc_fence_after_sync();
+                                }
+                                const uint32_t a_hi = tbase + col_a + 16u * kb;
+                                const uint64_t bhi = make_smem_desc(sbase + y.b_off[0][s] + kb * blk, lbo, 128);
+                                const uint64_t blo = make_smem_desc(sbase + y.b_off[1][s] + kb * blk, lbo, 128);
+                                mma_ts<2>(d_addr, a_hi, bhi, idesc, kb > 0);
+                                mma_ts<2>(d_addr, a_hi + 8, bhi, idesc, 1);
+                                mma_ts<2>(d_addr, a_hi, blo, idesc, 1);
+                            }
+                            mma_commit<2>(&bars[BAR_ACC + m * 2 + s], 0x3);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= kEpiWarps) {
+        // =========================================================== prep warps
+        const int ptid = tid - kEpiThreads;
+        mbar_wait(&bars[BAR_WLOAD], 0, 110);
+        for (int u = 0; u < T; ++u) {
+            const int b = u % kTcPrepBufs;
+            if (u >= kTcPrepBufs) mbar_wait(&bars[BAR_PREP_EMPTY + b], (uint32_t)((u / kTcPrepBufs - 1) & 1), 120 + b);
+            const long long row0 = (long long)u * kTcTile;
+            const long long ls_first = row0 / p.rps;
+            for (int r = ptid; r < kTcTile; r += kPrepThreads) {
+                const long long row = row0 + r;
+                float xi = 0.0f;
+                int rel = 0, node = -1;
+                if (row < n_rows) {
+                    const long long ls = row / p.rps;
+                    node = (int)(row - ls * p.rps);
+                    rel = (int)(ls - ls_first);
+                    const long long slot = slot_begin + ls;
+                    const float lo = p.x0 ? __ldg(p.x0 + slot) : 0.0f;
+                    const float hi = __ldg(p.x + slot);
+                    if (node <= p.Q) {
+                        const float xT = upper_limit(lo, hi, p.Q);
+                        xi = node_abscissa(lo, __fsub_rn(xT, lo), tab_t[node]);
+                    } else if (node == p.Q + 1 && p.out_fx) {
+                        xi = hi;
+                    } else {
+                        xi = lo;
+                    }
+                }
+                xnode[b * kTcTile + r] = xi;
+                lsrel[b * kTcTile + r] = rel;
+                nodeid[b * kTcTile + r] = node;
+            }
+            int ns = 1;
+            bool live = row0 < n_rows;
+            if (live) {
+                const long long last = (row0 + kTcTile < n_rows ? row0 + kTcTile : n_rows) - 1;
+                ns = (int)(last / p.rps - ls_first) + 1;
+            }
+            float* cv = cvec + (size_t)b * p.S.max_slots * L.npad1;
+            for (int idx = ptid; idx < ns * L.npad1; idx += kPrepThreads) {
+                const int i = idx / L.npad1, n = idx - i * L.npad1;
+                float acc = b1p[n];
+                if (live) {
+                    int hs;
+                    const float* hp = slot_ctx(p, slot_begin + ls_first + i, &hs);
+                    for (int e = 0; e < p.E; ++e) acc = fmaf(w1h[e * L.npad1 + n], __ldg(hp + (long long)e * hs), acc);
+                }
+                cv[i * L.npad1 + n] = acc;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[BAR_PREP_FULL + b]);
+        }
+    } else {
+        // =========================================================== epilogue warps
+        const int q = warp & 3, g = warp >> 2;
+        const int r = q * 32 + lane;                      // row of the tile owned by this thread
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        const int n_mma = L.n_mma;
+        const bool even_layers = (n_mma & 1) == 0;        // last accumulator shares region Q with layer 1's output
+        const int chunks1 = L.npad1 / 16, chunksL = L.npadL / 16;
+        const uint32_t col_last = ((n_mma - 1) & 1) ? kColQ : kColP;   // accumulator region of the last MMA layer
+        const TcMmaLayer& ylast = L.layer[n_mma - 1];
+        float carry = 0.0f;
+
+        mbar_wait(&bars[BAR_WLOAD], 0, 130);
+
+        // layer 1 of tile `u` (prep buffer bu), chunk j -> A operand of MMA layer 0 in region Q
+        auto l1_chunk = [&](int bu, int j) {
+            const float xn = xnode[bu * kTcTile + r];
+            const float* cv = cvec + ((size_t)bu * p.S.max_slots + lsrel[bu * kTcTile + r]) * L.npad1 + 16 * j;
+            const float* wx = w1x + 16 * j;
+            uint32_t o[16];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float a0 = hact<HIDDEN_ACT>(fmaf(xn, wx[2 * i], cv[2 * i]));
+                const float a1 = hact<HIDDEN_ACT>(fmaf(xn, wx[2 * i + 1], cv[2 * i + 1]));
+                split_bf16x2(a0, a1, o[i], o[8 + i]);
+            }
+            tmem_st16(tbase + lane_sel + kColQ + 16u * j, o);
+            tmem_st_wait();
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&bars[BAR_READY + 0 * 16 + j], 0);
+        };
+
+        // prologue: layer 1 of tile 0
+        mbar_wait(&bars[BAR_PREP_FULL + 0], 0, 131);
+        for (int j = g; j < chunks1; j += 2) l1_chunk(0, j);
+
+        for (int t = 0; t < T; ++t) {
+            const uint32_t par = (uint32_t)(t & 1);
+            const int b = t % kTcPrepBufs;
+            const bool has_next = (t + 1 < T);
+            const int bn = (t + 1) % kTcPrepBufs;
+
+            // ---- accumulator of MMA layer m -> A operand of layer m+1, in place
+            for (int m = 0; m + 1 < n_mma; ++m) {
+                const TcMmaLayer& y = L.layer[m];
+                const uint32_t col_d = (m & 1) ? kColQ : kColP;
+                const int n_chunks = y.npad / 16;
+                for (int j = g; j < n_chunks; j += 2) {
+                    const int s = (y.nseg == 2 && 16 * j >= y.seg_begin[1]) ? 1 : 0;
+                    mbar_wait(&bars[BAR_ACC + m * 2 + s], par, 300 + m * 2 + s);
+                    tc_fence_after_sync();
+                    uint32_t v[16], o[16];
+                    const uint32_t taddr = tbase + lane_sel + col_d + 16u * j;
+                    tmem_ld16(taddr, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        split_bf16x2(hact<HIDDEN_ACT>(__uint_as_float(v[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v[2 * i + 1])),
+                                     o[i], o[8 + i]);
+                    tmem_st16(taddr, o);
+                    tmem_st_wait();
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(&bars[BAR_READY + (m + 1) * 16 + j], 0);
+                }
+            }
+
+            // ---- last accumulator: output layer dot product; even layer counts also write layer 1 of the
+            //      next tile over the chunk just consumed
+            float partial = 0.0f;
+            if (has_next && even_layers) mbar_wait(&bars[BAR_PREP_FULL + bn], (uint32_t)(((t + 1) / kTcPrepBufs) & 1), 132);
+            const int n_loop = chunksL > chunks1 ? chunksL : chunks1;
+            for (int j = g; j < n_loop; j += 2) {
+                if (j < chunksL) {
+                    const int s = (ylast.nseg == 2 && 16 * j >= ylast.seg_begin[1]) ? 1 : 0;
+                    mbar_wait(&bars[BAR_ACC + (n_mma - 1) * 2 + s], par, 310 + s);
+                    tc_fence_after_sync();
+                    uint32_t v[16];
+                    tmem_ld16(tbase + lane_sel + col_last + 16u * j, v);
+                    tmem_ld_wait();
+                    const float* wv = w4 + 16 * j;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) partial = fmaf(hact<HIDDEN_ACT>(__uint_as_float(v[i])), wv[i], partial);
+                } else if (even_layers) {
+                    // columns beyond the last accumulator: free once every MMA of this tile is done
+                    for (int s = 0; s < ylast.nseg; ++s) mbar_wait(&bars[BAR_ACC + (n_mma - 1) * 2 + s], par, 320 + s);
+                    tc_fence_after_sync();
+                }
+                if (even_layers && has_next && j < chunks1) l1_chunk(bn, j);
+            }
+
+            // ---- finalize the rows of this tile
+            if (g == 1) part[r] = partial;
+            epi_bar_sync();
+            if (!even_layers && has_next) {
+                // odd layer counts: the last accumulator lives in P, which MMA layer 0 of the next tile
+                // overwrites -> publish layer 1 of the next tile only after every warp has read P
+                for (int s = 0; s < ylast.nseg; ++s) mbar_wait(&bars[BAR_ACC + (n_mma - 1) * 2 + s], par, 330 + s);
+                tc_fence_after_sync();
+                mbar_wait(&bars[BAR_PREP_FULL + bn], (uint32_t)(((t + 1) / kTcPrepBufs) & 1), 133);
+                for (int j = g; j < chunks1; j += 2) l1_chunk(bn, j);
+            }
+            const long long row0 = (long long)t * kTcTile;
+            if (g == 0) {
+                const int node = nodeid[b * kTcTile + r];
+                if (node >= 0) {
+                    const float f = out_act(partial + part[r], p.out_act);
+                    if (node <= p.Q) {
+                        fval[r] = f * tab_w[node];
+                    } else {
+                        const long long slot = slot_begin + (row0 + r) / p.rps;
+                        if (node == p.Q + 1 && p.out_fx) p.out_fx[slot] = f;
+                        else p.out_fx0[slot] = f;
+                    }
+                }
+            }
+            epi_bar_sync();
+            if (warp == 0 && row0 < n_rows) {
+                const long long last_row = (row0 + kTcTile < n_rows ? row0 + kTcTile : n_rows) - 1;
+                const long long s_first = row0 / p.rps, s_last = last_row / p.rps;
+                for (long long ls = s_first; ls <= s_last; ++ls) {
+                    const long long a = ls * p.rps, bb = a + p.Q;
+                    const long long lo = a > row0 ? a : row0;
+                    const long long hi = bb < last_row ? bb : last_row;
+                    float sum = 0.0f;
+                    for (long long rr = lo + lane; rr <= hi; rr += 32) sum += fval[(int)(rr - row0)];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                    if (lo <= hi) {
+                        const float total = (a < row0 ? carry : 0.0f) + sum;
+                        if (bb <= last_row) {
+                            if (lane == 0) {
+                                const long long slot = slot_begin + ls;
+                                const float x0v = p.x0 ? p.x0[slot] : 0.0f;
+                                const float span = __fsub_rn(upper_limit(x0v, p.x[slot], p.Q), x0v);
+                                p.out[slot] = __fmul_rn(__fmul_rn(total, span), 0.5f);
+                            }
+                            carry = 0.0f;
+                        } else {
+                            carry = total;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[BAR_PREP_EMPTY + b]);
+        }
+    }
+
+    // ---------------------------------------------------------------- teardown
+    tc_fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == kMmaWarp) tmem_dealloc<2>(tbase, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// parameter packing
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint16_t bf16_bits(float v) {
+    return (uint16_t)(pack_bf16x2(v, 0.0f) & 0xFFFFu);
+}
+__device__ __forceinline__ float bf16_val(float v) { return __uint_as_float((uint32_t)bf16_bits(v) << 16); }
+
+__global__ void pack_tc_weights_kernel(const float* __restrict__ flat, uint8_t* __restrict__ blobs, TcLayout L) {
+    const uint32_t per_rank = L.weights_bytes / 2;  // bf16 elements
+    const uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= 2 * per_rank) return;
+    const uint32_t rank = gi / per_rank;
+    const uint32_t byte_off = (gi - rank * per_rank) * 2;
+    // locate (layer, part, segment)
+    int m = 0, part = 0, s = 0;
+    bool found = false;
+    for (int mm = 0; mm < L.n_mma && !found; ++mm)
+        for (int pp = 0; pp < 2 && !found; ++pp)
+            for (int ss = 0; ss < L.layer[mm].nseg && !found; ++ss) {
+                const uint32_t lo = L.layer[mm].b_off[pp][ss];
+                const uint32_t sz = (uint32_t)(L.layer[mm].seg_n[ss] / 2) * L.layer[mm].kpad * 2;
+                if (byte_off >= lo && byte_off < lo + sz) { m = mm; part = pp; s = ss; found = true; }
+            }
+    const TcMmaLayer& y = L.layer[m];
+    const uint32_t idx = (byte_off - y.b_off[part][s]) / 2;
+    const int rows_cta = y.seg_n[s] / 2, n8c = rows_cta / 8;
+    const int per_kb = 2 * n8c * 64;
+    const int kb = idx / per_kb;
+    int rem = idx - kb * per_kb;
+    const int k8 = rem / (n8c * 64);
+    rem -= k8 * n8c * 64;
+    const int n8 = rem / 64;
+    const int rr = (rem % 64) / 8, kk = rem % 8;
+    const int n = y.seg_begin[s] + (int)rank * rows_cta + n8 * 8 + rr;
+    const int k = kb * 16 + k8 * 8 + kk;
+    const int lin = m + 1;  // Linear layer index in the flat vector
+    float hi = 0.0f, lo = 0.0f;
+    if (n < y.h_out) {
+        if (k < y.h_in) {
+            const float w = flat[L.src_w_off[lin] + n * y.h_in + k];
+            hi = bf16_val(w);
+            lo = bf16_val(w - hi);
+        } else if (k == y.h_in || k == y.h_in + 1) {
+            const float bv = flat[L.src_b_off[lin] + n];
+            const float b_hi = bf16_val(bv);
+            const float b_lo = bf16_val(bv - b_hi);
+            if (k == y.h_in) { hi = b_hi; lo = b_lo; }
+            else { hi = bf16_val(bv - b_hi - b_lo); lo = 0.0f; }
+        }
+    } else if ((n == y.h_out && k == y.h_in) || (n == y.h_out + 1 && k == y.h_in + 1)) {
+        hi = 1.0f;   // bias carriers propagate the constant 1
+    }
+    reinterpret_cast<uint16_t*>(blobs + (size_t)rank * L.blob_bytes)[byte_off / 2] = bf16_bits(part == 0 ? hi : lo);
+}
+
+__global__ void pack_tc_consts_kernel(const float* __restrict__ flat, uint8_t* __restrict__ blobs, TcLayout L, int n_layers) {
+    const uint32_t n_f = (L.blob_bytes - L.weights_bytes) / 4;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_f) return;
+    const uint32_t byte_off = L.weights_bytes + 4 * i;
+    float v = 0.0f;
+    const int nin0 = 1 + L.E;
+    if (byte_off >= L.off_w4) {
+        const int n = (byte_off - L.off_w4) / 4;
+        const int last = n_layers - 1;
+        if (n < L.hL) v = flat[L.src_w_off[last] + n];
+        else if (n == L.hL) v = flat[L.src_b_off[last]];
+    } else if (byte_off >= L.off_w1h) {
+        const int idx = (byte_off - L.off_w1h) / 4;
+        const int e = idx / L.npad1, n = idx % L.npad1;
+        if (n < L.h1 && e < L.E) v = flat[L.src_w_off[0] + n * nin0 + 1 + e];
+    } else if (byte_off >= L.off_b1p) {
+        const int n = (byte_off - L.off_b1p) / 4;
+        if (n < L.h1) v = flat[L.src_b_off[0] + n];
+        else if (n == L.h1 || n == L.h1 + 1) v = 1.0f;
+    } else {
+        const int n = (byte_off - L.off_w1x) / 4;
+        if (n < L.h1) v = flat[L.src_w_off[0] + n * nin0];
+    }
+    for (int rank = 0; rank < 2; ++rank) *reinterpret_cast<float*>(blobs + (size_t)rank * L.blob_bytes + byte_off) = v;
+}
+
+bool tc_two_segments() {
+    const char* e = getenv("UMNN_B200_TC_SEGMENTS");
+    return !(e && e[0] == '1');
+}
+
+}  // namespace
+
+const char* tc_unsupported_reason(const umnn_desc* d, int extra_rows) {
+    TcLayout L;
+    if (!make_tc_layout(d, &L, tc_two_segments())) return "needs >= 2 hidden layers of width <= 254";
+    const int rps = d->nb_steps + 1 + extra_rows;
+    const TcSmem S = make_tc_smem(L, rps, d->nb_steps);
+    if (S.total > kTcMaxSmem) return "weights + per-tile context do not fit in 227 KB of shared memory";
+    return nullptr;
+}
+
+int launch_pack_tc(const umnn_desc* d, const float* flat, void* packed, cudaStream_t s) {
+    TcLayout L;
+    if (!make_tc_layout(d, &L, tc_two_segments())) {
+        set_error("BF16X3: shape not supported by the tensor-core kernel");
+        return UMNN_ERR_UNSUPPORTED;
+    }
+    const uint32_t n_w = L.weights_bytes;  // = 2 ranks x weights_bytes/2 elements
+    pack_tc_weights_kernel<<<(n_w + 255) / 256, 256, 0, s>>>(flat, (uint8_t*)packed, L);
+    UMNN_CUDA_TRY(cudaGetLastError());
+    const uint32_t n_f = (L.blob_bytes - L.weights_bytes) / 4;
+    pack_tc_consts_kernel<<<(n_f + 255) / 256, 256, 0, s>>>(flat, (uint8_t*)packed, L, d->n_layers);
+    UMNN_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+size_t tc_packed_bytes(const umnn_desc* d) {
+    TcLayout L;
+    if (!make_tc_layout(d, &L, tc_two_segments())) return 0;
+    return 2 * (size_t)L.blob_bytes;
+}
+
+int launch_forward_tc(const umnn_desc* d, const float* x0, const float* x, const float* h, const void* packed,
+                      const float* nodes, const float* weights, float* out, float* out_fx, float* out_fx0,
+                      cudaStream_t s) {
+    TcParams p{};
+    if (!make_tc_layout(d, &p.L, tc_two_segments())) {
+        set_error("BF16X3: shape not supported by the tensor-core kernel");
+        return UMNN_ERR_UNSUPPORTED;
+    }
+    p.x0 = x0; p.x = x; p.h = h; p.nodes = nodes; p.weights = weights; p.blobs = (const uint8_t*)packed;
+    p.out = out; p.out_fx = out_fx; p.out_fx0 = out_fx0;
+    p.n_slots = d->n_samples * (long long)d->n_dims;
+    p.D = d->n_dims; p.E = d->n_ctx; p.layout = d->layout; p.Q = d->nb_steps; p.out_act = d->out_act;
+    p.rps = d->nb_steps + 1 + (out_fx ? 1 : 0) + (out_fx0 ? 1 : 0);
+    p.S = make_tc_smem(p.L, p.rps, p.Q);
+    if (p.S.total > kTcMaxSmem) {
+        set_error("BF16X3: needs %u bytes of shared memory (max %zu)", p.S.total, kTcMaxSmem);
+        return UMNN_ERR_UNSUPPORTED;
+    }
+    if (p.n_slots == 0) return 0;
+    int dev = 0, n_sm = 0;
+    UMNN_CUDA_TRY(cudaGetDevice(&dev));
+    UMNN_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    const long long total_rows = p.n_slots * p.rps;
+    long long n_cta = (total_rows + kTcTile - 1) / kTcTile;
+    const long long cap = (long long)(n_sm / 2) * 2;
+    if (n_cta > cap) n_cta = cap;
+    if (n_cta > p.n_slots) n_cta = p.n_slots;
+    n_cta = (n_cta + 1) / 2 * 2;             // whole CTA pairs
+    if (n_cta < 2) n_cta = 2;
+    p.slots_per_cta = (p.n_slots + n_cta - 1) / n_cta;
+    p.tiles_per_cta = (int)((p.slots_per_cta * p.rps + kTcTile - 1) / kTcTile);
+
+    auto kern = d->hidden_act == UMNN_ACT_LEAKY_RELU ? cc_forward_tc_kernel<UMNN_ACT_LEAKY_RELU>
+                                                     : cc_forward_tc_kernel<UMNN_ACT_RELU>;
+    UMNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.S.total));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)n_cta);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = p.S.total;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    UMNN_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
+    return 0;
+}
+
+}  // namespace umnn

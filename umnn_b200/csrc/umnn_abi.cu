@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "umnn_common.cuh"
+#include "tc_layout.cuh"
 
 namespace umnn {
 
@@ -74,11 +75,21 @@ int validate_desc(const umnn_desc* d) {
     return 0;
 }
 
-// Which kernel family serves this descriptor.  UMNN_PREC_AUTO resolves to FP32 until the BF16x3
-// tensor-core kernel covers the shape.
+// Which kernel family serves this descriptor.  UMNN_PREC_AUTO picks the BF16x3 tensor-core kernel
+// whenever the shape fits it (checked with the worst-case 2 extra rows per slot so that packing and
+// launching agree), else the FP32 kernel.  An explicit UMNN_PREC_BF16X3 on an unsupported shape fails.
 static int resolve_precision(const umnn_desc* d) {
-    if (d->precision == UMNN_PREC_AUTO) return UMNN_PREC_FP32;
+    if (d->precision == UMNN_PREC_AUTO) return tc_unsupported_reason(d, 2) == nullptr ? UMNN_PREC_BF16X3 : UMNN_PREC_FP32;
     return d->precision;
+}
+
+static int check_tc(const umnn_desc* d, const char* who) {
+    const char* why = tc_unsupported_reason(d, 2);
+    if (why) {
+        set_error("%s: UMNN_PREC_BF16X3 unavailable for this shape (%s)", who, why);
+        return UMNN_ERR_UNSUPPORTED;
+    }
+    return 0;
 }
 
 }  // namespace umnn
@@ -125,6 +136,7 @@ size_t umnn_packed_params_bytes(const umnn_desc* d) {
     if (validate_desc(d) != 0) return 0;
     switch (resolve_precision(d)) {
         case UMNN_PREC_FP32: return sizeof(float) * (size_t)make_fp32_layout(d).total_floats;
+        case UMNN_PREC_BF16X3: return check_tc(d, "umnn_packed_params_bytes") ? 0 : tc_packed_bytes(d);
         default: return 0;
     }
 }
@@ -136,6 +148,9 @@ int umnn_pack_params(const umnn_desc* d, const float* flat_params, void* params_
     switch (resolve_precision(d)) {
         case UMNN_PREC_FP32:
             return launch_pack_fp32(d, flat_params, (float*)params_packed, (cudaStream_t)stream);
+        case UMNN_PREC_BF16X3:
+            if ((rc = check_tc(d, "umnn_pack_params")) != 0) return rc;
+            return launch_pack_tc(d, flat_params, params_packed, (cudaStream_t)stream);
         default:
             set_error("umnn_pack_params: precision %d is not available for this shape", d->precision);
             return UMNN_ERR_UNSUPPORTED;
@@ -162,6 +177,10 @@ int umnn_cc_forward(const umnn_desc* d, const float* x0, const float* x, const f
         case UMNN_PREC_FP32:
             return launch_forward_fp32(d, x0, x, h, (const float*)params_packed, nodes, weights, out_integral,
                                        out_f_at_x, out_f_at_x0, (cudaStream_t)stream);
+        case UMNN_PREC_BF16X3:
+            if ((rc = check_tc(d, "umnn_cc_forward")) != 0) return rc;
+            return launch_forward_tc(d, x0, x, h, params_packed, nodes, weights, out_integral, out_f_at_x,
+                                     out_f_at_x0, (cudaStream_t)stream);
         default:
             set_error("umnn_cc_forward: precision %d is not available for this shape", d->precision);
             return UMNN_ERR_UNSUPPORTED;

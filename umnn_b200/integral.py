@@ -285,12 +285,13 @@ class NeuralIntegral(torch.autograd.Function):
         return d_x0, d_x, None, d_flat, d_h, None
 
 
-def cc_integrate(integrand, x0, x, h, nb_steps, want_fx=False, want_fx0=False):
+def cc_integrate(integrand, x0, x, h, nb_steps, want_fx=False, want_fx0=False, precision=None):
     """Functional, value-only entry of the fused kernel: (integral, f(x,h) | None, f(x0,h) | None).
 
     One launch gives the integral of UMNNMAF.forward (UMNNMAF.py:76-134) and the Jacobian point of
     UMNNMAF.compute_log_jac (:136-139).  CUDA float32 tensors and a recognised integrand are
-    required -- this entry never takes the torch route.
+    required -- this entry never takes the torch route.  `precision`: None (UMNN_B200_PRECISION or auto),
+    or one of umnn_b200._native.PREC_FP32 / PREC_BF16X3 / PREC_AUTO.
     """
     if x0 is None:
         x0_probe = x
@@ -301,4 +302,4 @@ def cc_integrate(integrand, x0, x, h, nb_steps, want_fx=False, want_fx0=False):
         raise ValueError("cc_integrate needs CUDA float32 tensors and a recognised integrand "
                          "(IntegrandNetwork, IntegrandNN, ContiguousIntegrand) within the kernel's limits")
     with torch.no_grad():
-        return kernel.cc_forward(spec, x0, x, h, nb_steps, want_fx=want_fx, want_fx0=want_fx0)
+        return kernel.cc_forward(spec, x0, x, h, nb_steps, want_fx=want_fx, want_fx0=want_fx0, precision=precision)
