@@ -17,8 +17,9 @@
 //   output layer dot product on CUDA cores while the last accumulator is read, ELU+1, CC weight,
 //                deterministic segmented sum per slot, (z*(xT-x0))/2.
 //
-// Warp roles per CTA (384 threads): warps 0-7 epilogue (TMEM lane quadrant = warp%4, even/odd 16-column
-// chunks = warp/4), warps 8-10 "prep" (abscissae + c_slot for the tile two ahead), warp 11 MMA issuer.
+// Warp roles per CTA (640 threads): warps 0-15 epilogue (TMEM lane quadrant = warp%4; warp/4 selects which
+// 32-column pairs of K blocks it converts), warps 16-18 "prep" (abscissae + c_slot, running tiles ahead),
+// warp 19 MMA issuer (one elected lane of the leader CTA).
 #include "tc_common.cuh"
 #include "tc_layout.cuh"
 
@@ -30,17 +31,18 @@ namespace {
 
 using namespace tc;
 
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;                       // 4 per TMEM lane quadrant
+constexpr int kColGroups = kEpiWarps / 4;           // column groups: warp/4 handles 32-column pairs p % 4 == warp/4
 constexpr int kPrepWarps = 3;
 constexpr int kMmaWarp = kEpiWarps + kPrepWarps;
-constexpr int kThreads = (kMmaWarp + 1) * 32;
+constexpr int kThreads = (kMmaWarp + 1) * 32;       // 640
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kPrepThreads = kPrepWarps * 32;
 constexpr uint32_t kColP = 0, kColQ = kTcRegionCols;
 
 // barrier indices
-constexpr int BAR_READY = 0;                                   // [layer][16]
-constexpr int BAR_ACC = BAR_READY + kTcMaxMmaLayers * 16;      // [layer][2]
+constexpr int BAR_READY = 0;                                   // [layer][8]  A-operand pair p of MMA layer m is in TMEM
+constexpr int BAR_ACC = BAR_READY + kTcMaxMmaLayers * 8;       // [layer][2]  accumulator segment s of layer m complete
 constexpr int BAR_PREP_FULL = BAR_ACC + kTcMaxMmaLayers * 2;   // [kTcPrepBufs]
 constexpr int BAR_PREP_EMPTY = BAR_PREP_FULL + kTcPrepBufs;    // [kTcPrepBufs]
 constexpr int BAR_WLOAD = BAR_PREP_EMPTY + kTcPrepBufs;
@@ -73,6 +75,7 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 }
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"r"(kEpiThreads) : "memory"); }
+__device__ __forceinline__ void prep_bar_sync() { asm volatile("bar.sync 2, %0;" ::"r"(kPrepThreads) : "memory"); }
 
 __device__ __forceinline__ const float* slot_ctx(const TcParams& p, long long slot, int* stride) {
     if (p.layout == UMNN_LAYOUT_STRIDED_D) {
@@ -101,10 +104,11 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
     const int T = p.tiles_per_cta;
 
     float* cvec = reinterpret_cast<float*>(smem + p.S.off_cvec);      // [bufs][max_slots][npad1]
+    float* hbuf = reinterpret_cast<float*>(smem + p.S.off_hbuf);      // [max_slots][E]
     float* xnode = reinterpret_cast<float*>(smem + p.S.off_xnode);    // [bufs][128]
     int* lsrel = reinterpret_cast<int*>(smem + p.S.off_lsrel);        // [bufs][128]
     int* nodeid = reinterpret_cast<int*>(smem + p.S.off_node);        // [bufs][128]
-    float* part = reinterpret_cast<float*>(smem + p.S.off_part);      // [128]
+    float* part = reinterpret_cast<float*>(smem + p.S.off_part);      // [3][128]
     float* fval = reinterpret_cast<float*>(smem + p.S.off_fval);      // [128]
     float* tab_t = reinterpret_cast<float*>(smem + p.S.off_tabt);
     float* tab_w = reinterpret_cast<float*>(smem + p.S.off_tabw);
@@ -123,7 +127,7 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
     // ---------------------------------------------------------------- setup
     if (tid == 0) {
         for (int m = 0; m < kTcMaxMmaLayers; ++m) {
-            for (int j = 0; j < 16; ++j) mbar_init(&bars[BAR_READY + m * 16 + j], 8);   // 4 warps x 2 CTAs
+            for (int j = 0; j < 8; ++j) mbar_init(&bars[BAR_READY + m * 8 + j], 8);     // 4 quadrant warps x 2 CTAs
             for (int s = 0; s < 2; ++s) mbar_init(&bars[BAR_ACC + m * 2 + s], 1);       // tcgen05.commit
         }
         for (int b = 0; b < kTcPrepBufs; ++b) {
@@ -147,7 +151,9 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
 
     if (warp == kMmaWarp) {
         // =========================================================== MMA issuer warp
-        if (lane == 0) {
+        // The whole warp runs this code converged (uniform control flow keeps descriptors and TMEM
+        // addresses in uniform registers); one elected lane issues the tcgen05 instructions.
+        if (elect_one_sync()) {
             // stage this CTA's parameter blob with bulk-TMA copies (<= 32 KB each) on one mbarrier
             mbar_expect_tx(&bars[BAR_WLOAD], L.blob_bytes);
             const uint8_t* src = p.blobs + (size_t)rank * L.blob_bytes;
@@ -155,37 +161,47 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
                 const uint32_t n = (L.blob_bytes - off < 32768u) ? (L.blob_bytes - off) : 32768u;
                 bulk_g2s(smem + off, src + off, n, &bars[BAR_WLOAD]);
             }
-            mbar_wait(&bars[BAR_WLOAD], 0, 100);
-            mbar_arrive_cluster(&bars[BAR_PEER], 0);    // tell the leader this CTA's half of B is resident
-            if (rank == 0) {
-                mbar_wait_cluster(&bars[BAR_PEER], 0, 101);
-                const uint32_t sbase = smem_u32(smem);
-                for (int t = 0; t < T; ++t) {
-                    const uint32_t par = (uint32_t)(t & 1);
-                    for (int m = 0; m < L.n_mma; ++m) {
-                        const TcMmaLayer& y = L.layer[m];
-                        const uint32_t col_a = (m & 1) ? kColP : kColQ;   // A operand region
-                        const uint32_t col_d = (m & 1) ? kColQ : kColP;   // accumulator region
-                        const int n_kb = y.kpad / 16;
-                        for (int s = 0; s < y.nseg; ++s) {
-                            const uint32_t idesc = make_idesc_bf16_f32(256, y.seg_n[s]);
-                            const uint32_t lbo = (uint32_t)(y.seg_n[s] / 16) * 128u;
-                            const uint32_t blk = 2u * lbo;
-                            const uint32_t d_addr = tbase + col_d + (uint32_t)y.seg_begin[s];
-                            for (int kb = 0; kb < n_kb; ++kb) {
-                                if (s == 0) {
-                                    mbar_wait_cluster(&bars[BAR_READY + m * 16 + kb], par, 200 + m * 16 + kb);
-                                    tc_fence_after_sync();
-                                }
-                                const uint32_t a_hi = tbase + col_a + 16u * kb;
-                                const uint64_t bhi = make_smem_desc(sbase + y.b_off[0][s] + kb * blk, lbo, 128);
-                                const uint64_t blo = make_smem_desc(sbase + y.b_off[1][s] + kb * blk, lbo, 128);
+        }
+        __syncwarp();
+        mbar_wait(&bars[BAR_WLOAD], 0, 100);
+        if (elect_one_sync()) mbar_arrive_cluster(&bars[BAR_PEER], 0);   // this CTA's half of B is resident
+        __syncwarp();
+        if (rank == 0) {
+            mbar_wait(&bars[BAR_PEER], 0, 101);
+            const uint32_t sbase = smem_u32(smem);
+            for (int t = 0; t < T; ++t) {
+                const uint32_t par = (uint32_t)(t & 1);
+                for (int m = 0; m < L.n_mma; ++m) {
+                    const TcMmaLayer& y = L.layer[m];
+                    const uint32_t a_base = tbase + ((m & 1) ? kColP : kColQ);   // A operand region
+                    const uint32_t col_d = (m & 1) ? kColQ : kColP;             // accumulator region
+                    const int n_kb = y.kpad / 16;
+                    uint64_t* ready = &bars[BAR_READY + m * 8];
+                    for (int s = 0; s < y.nseg; ++s) {
+                        const uint32_t idesc = make_idesc_bf16_f32(256, y.seg_n[s]);
+                        const uint32_t lbo = (uint32_t)(y.seg_n[s] / 16) * 128u;
+                        const uint64_t step = (uint64_t)((2u * lbo) >> 4);        // descriptor address field is in 16-byte units
+                        const uint32_t d_addr = tbase + col_d + (uint32_t)y.seg_begin[s];
+                        uint64_t bhi = make_smem_desc(sbase + y.b_off[0][s], lbo, 128);
+                        uint64_t blo = make_smem_desc(sbase + y.b_off[1][s], lbo, 128);
+                        uint32_t a_hi = a_base;
+                        for (int kb = 0; kb < n_kb; ++kb) {
+                            if (s == 0 && (kb & 1) == 0) {
+                                mbar_wait(&ready[kb >> 1], par, 200 + m * 8 + (kb >> 1));
+                                tc_fence_after_sync();
+                            }
+                            if (elect_one_sync()) {
                                 mma_ts<2>(d_addr, a_hi, bhi, idesc, kb > 0);
                                 mma_ts<2>(d_addr, a_hi + 8, bhi, idesc, 1);
                                 mma_ts<2>(d_addr, a_hi, blo, idesc, 1);
                             }
-                            mma_commit<2>(&bars[BAR_ACC + m * 2 + s], 0x3);
+                            __syncwarp();
+                            a_hi += 16;
+                            bhi += step;
+                            blo += step;
                         }
+                        if (elect_one_sync()) mma_commit<2>(&bars[BAR_ACC + m * 2 + s], 0x3);
+                        __syncwarp();
                     }
                 }
             }
@@ -200,6 +216,20 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
             if (u >= kTcPrepBufs) mbar_wait(&bars[BAR_PREP_EMPTY + b], (uint32_t)((u / kTcPrepBufs - 1) & 1), 120 + b);
             const long long row0 = (long long)u * kTcTile;
             const long long ls_first = row0 / p.rps;
+            const bool live = row0 < n_rows;
+            int ns = 1;
+            if (live) {
+                const long long last = (row0 + kTcTile < n_rows ? row0 + kTcTile : n_rows) - 1;
+                ns = (int)(last / p.rps - ls_first) + 1;
+            }
+            // context of the slots this tile touches -> shared memory (one gather per value)
+            if (live)
+                for (int idx = ptid; idx < ns * p.E; idx += kPrepThreads) {
+                    const int i = idx / p.E, e = idx - i * p.E;
+                    int hs;
+                    const float* hp = slot_ctx(p, slot_begin + ls_first + i, &hs);
+                    hbuf[idx] = __ldg(hp + (long long)e * hs);
+                }
             for (int r = ptid; r < kTcTile; r += kPrepThreads) {
                 const long long row = row0 + r;
                 float xi = 0.0f;
@@ -224,45 +254,39 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
                 lsrel[b * kTcTile + r] = rel;
                 nodeid[b * kTcTile + r] = node;
             }
-            int ns = 1;
-            bool live = row0 < n_rows;
-            if (live) {
-                const long long last = (row0 + kTcTile < n_rows ? row0 + kTcTile : n_rows) - 1;
-                ns = (int)(last / p.rps - ls_first) + 1;
-            }
+            prep_bar_sync();
             float* cv = cvec + (size_t)b * p.S.max_slots * L.npad1;
             for (int idx = ptid; idx < ns * L.npad1; idx += kPrepThreads) {
                 const int i = idx / L.npad1, n = idx - i * L.npad1;
                 float acc = b1p[n];
                 if (live) {
-                    int hs;
-                    const float* hp = slot_ctx(p, slot_begin + ls_first + i, &hs);
-                    for (int e = 0; e < p.E; ++e) acc = fmaf(w1h[e * L.npad1 + n], __ldg(hp + (long long)e * hs), acc);
+                    const float* hv = hbuf + i * p.E;
+                    for (int e = 0; e < p.E; ++e) acc = fmaf(w1h[e * L.npad1 + n], hv[e], acc);
                 }
                 cv[i * L.npad1 + n] = acc;
             }
-            __syncwarp();
+            prep_bar_sync();   // hbuf is rewritten by the next tile
             if (lane == 0) mbar_arrive(&bars[BAR_PREP_FULL + b]);
         }
     } else {
         // =========================================================== epilogue warps
-        const int q = warp & 3, g = warp >> 2;
+        const int q = warp & 3, cg = warp >> 2;
         const int r = q * 32 + lane;                      // row of the tile owned by this thread
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
         const int n_mma = L.n_mma;
         const bool even_layers = (n_mma & 1) == 0;        // last accumulator shares region Q with layer 1's output
-        const int chunks1 = L.npad1 / 16, chunksL = L.npadL / 16;
+        const int pairs1 = (L.npad1 + 31) / 32, pairsL = (L.npadL + 31) / 32;
         const uint32_t col_last = ((n_mma - 1) & 1) ? kColQ : kColP;   // accumulator region of the last MMA layer
         const TcMmaLayer& ylast = L.layer[n_mma - 1];
         float carry = 0.0f;
 
         mbar_wait(&bars[BAR_WLOAD], 0, 130);
 
-        // layer 1 of tile `u` (prep buffer bu), chunk j -> A operand of MMA layer 0 in region Q
-        auto l1_chunk = [&](int bu, int j) {
+        // one 16-column half of layer 1 for the tile in prep buffer `bu` -> A operand of MMA layer 0 (region Q)
+        auto l1_half = [&](int bu, int c16) {
             const float xn = xnode[bu * kTcTile + r];
-            const float* cv = cvec + ((size_t)bu * p.S.max_slots + lsrel[bu * kTcTile + r]) * L.npad1 + 16 * j;
-            const float* wx = w1x + 16 * j;
+            const float* cv = cvec + ((size_t)bu * p.S.max_slots + lsrel[bu * kTcTile + r]) * L.npad1 + 16 * c16;
+            const float* wx = w1x + 16 * c16;
             uint32_t o[16];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -270,16 +294,24 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
                 const float a1 = hact<HIDDEN_ACT>(fmaf(xn, wx[2 * i + 1], cv[2 * i + 1]));
                 split_bf16x2(a0, a1, o[i], o[8 + i]);
             }
-            tmem_st16(tbase + lane_sel + kColQ + 16u * j, o);
+            tmem_st16(tbase + lane_sel + kColQ + 16u * c16, o);
+        };
+        // publish pair `pp` of MMA layer `m`'s A operand (both CTAs arrive on the leader's barrier)
+        auto publish = [&](int m, int pp) {
             tmem_st_wait();
             tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(&bars[BAR_READY + 0 * 16 + j], 0);
+            if (lane == 0) mbar_arrive_cluster(&bars[BAR_READY + m * 8 + pp], 0);
+        };
+        auto l1_pair = [&](int bu, int pp) {
+            l1_half(bu, 2 * pp);
+            if (32 * pp + 16 < L.npad1) l1_half(bu, 2 * pp + 1);
+            publish(0, pp);
         };
 
         // prologue: layer 1 of tile 0
         mbar_wait(&bars[BAR_PREP_FULL + 0], 0, 131);
-        for (int j = g; j < chunks1; j += 2) l1_chunk(0, j);
+        for (int pp = cg; pp < pairs1; pp += kColGroups) l1_pair(0, pp);
 
         for (int t = 0; t < T; ++t) {
             const uint32_t par = (uint32_t)(t & 1);
@@ -291,53 +323,66 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
             for (int m = 0; m + 1 < n_mma; ++m) {
                 const TcMmaLayer& y = L.layer[m];
                 const uint32_t col_d = (m & 1) ? kColQ : kColP;
-                const int n_chunks = y.npad / 16;
-                for (int j = g; j < n_chunks; j += 2) {
-                    const int s = (y.nseg == 2 && 16 * j >= y.seg_begin[1]) ? 1 : 0;
+                const int n_pairs = (y.npad + 31) / 32;
+                for (int pp = cg; pp < n_pairs; pp += kColGroups) {
+                    const int s = (y.nseg == 2 && 32 * pp >= y.seg_begin[1]) ? 1 : 0;
                     mbar_wait(&bars[BAR_ACC + m * 2 + s], par, 300 + m * 2 + s);
                     tc_fence_after_sync();
-                    uint32_t v[16], o[16];
-                    const uint32_t taddr = tbase + lane_sel + col_d + 16u * j;
-                    tmem_ld16(taddr, v);
+                    const uint32_t taddr = tbase + lane_sel + col_d + 32u * pp;
+                    const bool two = 32 * pp + 16 < y.npad;
+                    uint32_t v0[16], v1[16], o[16];
+                    tmem_ld16(taddr, v0);
+                    if (two) tmem_ld16(taddr + 16, v1);
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
-                        split_bf16x2(hact<HIDDEN_ACT>(__uint_as_float(v[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v[2 * i + 1])),
+                        split_bf16x2(hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i + 1])),
                                      o[i], o[8 + i]);
                     tmem_st16(taddr, o);
-                    tmem_st_wait();
-                    tc_fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(&bars[BAR_READY + (m + 1) * 16 + j], 0);
+                    if (two) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            split_bf16x2(hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i + 1])),
+                                         o[i], o[8 + i]);
+                        tmem_st16(taddr + 16, o);
+                    }
+                    publish(m + 1, pp);
                 }
             }
 
             // ---- last accumulator: output layer dot product; even layer counts also write layer 1 of the
-            //      next tile over the chunk just consumed
+            //      next tile over the pair just consumed
             float partial = 0.0f;
             if (has_next && even_layers) mbar_wait(&bars[BAR_PREP_FULL + bn], (uint32_t)(((t + 1) / kTcPrepBufs) & 1), 132);
-            const int n_loop = chunksL > chunks1 ? chunksL : chunks1;
-            for (int j = g; j < n_loop; j += 2) {
-                if (j < chunksL) {
-                    const int s = (ylast.nseg == 2 && 16 * j >= ylast.seg_begin[1]) ? 1 : 0;
+            const int n_loop = pairsL > pairs1 ? pairsL : pairs1;
+            for (int pp = cg; pp < n_loop; pp += kColGroups) {
+                if (pp < pairsL) {
+                    const int s = (ylast.nseg == 2 && 32 * pp >= ylast.seg_begin[1]) ? 1 : 0;
                     mbar_wait(&bars[BAR_ACC + (n_mma - 1) * 2 + s], par, 310 + s);
                     tc_fence_after_sync();
-                    uint32_t v[16];
-                    tmem_ld16(tbase + lane_sel + col_last + 16u * j, v);
+                    const uint32_t taddr = tbase + lane_sel + col_last + 32u * pp;
+                    const bool two = 32 * pp + 16 < L.npadL;
+                    uint32_t v0[16], v1[16];
+                    tmem_ld16(taddr, v0);
+                    if (two) tmem_ld16(taddr + 16, v1);
                     tmem_ld_wait();
-                    const float* wv = w4 + 16 * j;
+                    const float* wv = w4 + 32 * pp;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) partial = fmaf(hact<HIDDEN_ACT>(__uint_as_float(v[i])), wv[i], partial);
+                    for (int i = 0; i < 16; ++i) partial = fmaf(hact<HIDDEN_ACT>(__uint_as_float(v0[i])), wv[i], partial);
+                    if (two) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) partial = fmaf(hact<HIDDEN_ACT>(__uint_as_float(v1[i])), wv[16 + i], partial);
+                    }
                 } else if (even_layers) {
                     // columns beyond the last accumulator: free once every MMA of this tile is done
                     for (int s = 0; s < ylast.nseg; ++s) mbar_wait(&bars[BAR_ACC + (n_mma - 1) * 2 + s], par, 320 + s);
                     tc_fence_after_sync();
                 }
-                if (even_layers && has_next && j < chunks1) l1_chunk(bn, j);
+                if (even_layers && has_next && pp < pairs1) l1_pair(bn, pp);
             }
 
             // ---- finalize the rows of this tile
-            if (g == 1) part[r] = partial;
+            if (cg > 0) part[(cg - 1) * kTcTile + r] = partial;
             epi_bar_sync();
             if (!even_layers && has_next) {
                 // odd layer counts: the last accumulator lives in P, which MMA layer 0 of the next tile
@@ -345,13 +390,13 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
                 for (int s = 0; s < ylast.nseg; ++s) mbar_wait(&bars[BAR_ACC + (n_mma - 1) * 2 + s], par, 330 + s);
                 tc_fence_after_sync();
                 mbar_wait(&bars[BAR_PREP_FULL + bn], (uint32_t)(((t + 1) / kTcPrepBufs) & 1), 133);
-                for (int j = g; j < chunks1; j += 2) l1_chunk(bn, j);
+                for (int pp = cg; pp < pairs1; pp += kColGroups) l1_pair(bn, pp);
             }
             const long long row0 = (long long)t * kTcTile;
-            if (g == 0) {
+            if (cg == 0) {
                 const int node = nodeid[b * kTcTile + r];
                 if (node >= 0) {
-                    const float f = out_act(partial + part[r], p.out_act);
+                    const float f = out_act(((partial + part[r]) + part[kTcTile + r]) + part[2 * kTcTile + r], p.out_act);
                     if (node <= p.Q) {
                         fval[r] = f * tab_w[node];
                     } else {

@@ -41,10 +41,12 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// arrive on the barrier at the same offset in CTA `rank` of the cluster (release at cluster scope)
+// arrive on the barrier at the same offset in CTA `rank` of the cluster.  Default (.release.cta) semantics:
+// the payload travels through tensor memory and is ordered by tcgen05.wait::st + tcgen05.fence, so no
+// cluster-scope memory fence (a full MEMBAR) is paid per arrive.
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
     const uint32_t remote = map_to_cta(smem_u32(bar), rank);
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -96,6 +98,17 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
     (void)tag;
     while (!mbar_try_wait_cluster(bar, parity)) {}
 #endif
+}
+
+// true in exactly one (elected) lane of a fully converged warp
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
 
 // generic-proxy writes to shared memory -> visible to the async proxy (tensor core / TMA reads)

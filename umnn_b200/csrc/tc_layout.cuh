@@ -81,13 +81,16 @@ inline bool make_tc_layout(const umnn_desc* d, TcLayout* L, bool two_segments = 
         y.h_out = d->widths[m + 2];
         y.kpad = tc_pad(y.h_in);
         y.npad = tc_pad(y.h_out);
-        const int units = y.npad / 16;
-        if (two_segments && units >= 2) {
+        // segments are cut at a multiple of 32 columns (the epilogue works on 32-column pairs of K blocks);
+        // a second segment narrower than 32 columns is not worth a separate MMA shape
+        const int pairs = (y.npad + 31) / 32;
+        const int n0 = 32 * ((pairs + 1) / 2);
+        if (two_segments && y.npad - n0 >= 32) {
             y.nseg = 2;
-            y.seg_n[0] = 16 * ((units + 1) / 2);
-            y.seg_n[1] = y.npad - y.seg_n[0];
+            y.seg_n[0] = n0;
+            y.seg_n[1] = y.npad - n0;
             y.seg_begin[0] = 0;
-            y.seg_begin[1] = y.seg_n[0];
+            y.seg_begin[1] = n0;
         } else {
             y.nseg = 1;
             y.seg_n[0] = y.npad;
@@ -112,22 +115,23 @@ inline bool make_tc_layout(const umnn_desc* d, TcLayout* L, bool two_segments = 
 
 // dynamic shared memory map of the forward kernel (byte offsets from the 1024-aligned base)
 struct TcSmem {
-    uint32_t off_cvec, off_xnode, off_lsrel, off_node, off_part, off_fval, off_tabt, off_tabw, off_bars, off_holder;
+    uint32_t off_cvec, off_hbuf, off_xnode, off_lsrel, off_node, off_part, off_fval, off_tabt, off_tabw, off_bars, off_holder;
     uint32_t total;
     int max_slots;
 };
 
-constexpr int kTcNumBars = kTcMaxMmaLayers * 18 /*ready[layer][16] + acc_full[layer][2]*/ + 2 * kTcPrepBufs + 2;
+constexpr int kTcNumBars = kTcMaxMmaLayers * 10 /*ready[layer][8 pairs] + acc_full[layer][2]*/ + 2 * kTcPrepBufs + 2;
 
 inline TcSmem make_tc_smem(const TcLayout& L, int rps, int Q) {
     TcSmem S{};
     S.max_slots = (kTcTile - 1) / rps + 2;   // slots a 128-row window can touch
     uint32_t off = L.blob_bytes;
     S.off_cvec = off;   off += 4u * kTcPrepBufs * S.max_slots * L.npad1;
+    S.off_hbuf = off;   off += 4u * S.max_slots * (L.E > 0 ? L.E : 1);
     S.off_xnode = off;  off += 4u * kTcPrepBufs * kTcTile;
     S.off_lsrel = off;  off += 4u * kTcPrepBufs * kTcTile;
     S.off_node = off;   off += 4u * kTcPrepBufs * kTcTile;
-    S.off_part = off;   off += 4u * kTcTile;
+    S.off_part = off;   off += 4u * 3 * kTcTile;
     S.off_fval = off;   off += 4u * kTcTile;
     S.off_tabt = off;   off += 4u * (Q + 1);
     S.off_tabw = off;   off += 4u * (Q + 1);
