@@ -233,7 +233,7 @@ def run_ours(args, cfg, name):
         for p in net.parameters():
             p.copy_(torch.from_numpy(flat[off:off + p.numel()].copy()).view_as(p))
             off += p.numel()
-    net.to(dev)
+    net.to(dev).eval()     # inference-style step: packed parameters are cached, ONE kernel launch per step
 
     # every rank owns its own shard of the global batch (B samples per GPU): weak scaling, no collective
     gen = torch.Generator(device="cpu").manual_seed(1000 + rank)
@@ -314,6 +314,14 @@ def run_ours(args, cfg, name):
     achieved_tflops = (rows_per_step / world) * fpe / (ms_per_step * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
     slot_bytes = 4 * (E + 1) + 8            # x, h read (x0 = NULL); integral, f(x) written
+    traffic = None
+    tpath = os.path.join(REPO, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from an `ncu --set full` capture of this
+        # workload / kernel (scripts/gpu_round.sh), recorded per slot so it scales with the batch
+        rec = json.load(open(tpath)).get(f"{name}:{'tc' if use_tc else 'fp32'}")
+        if rec:
+            traffic = rec["dram_bytes_per_slot"] * B * D
     out = {
         "metric": "integrand-evals/sec (B*D*Q)", "value": value, "unit": "integrand-evals/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -332,7 +340,8 @@ def run_ours(args, cfg, name):
         "gpu_launches": args.steps * world,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved_tflops / peak, "traffic": None,
+                     "frac": achieved_tflops / peak, "traffic": traffic,
+                     "algorithmic_bytes": B * D * slot_bytes,
                      "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
                      "flop_per_row": fpe, "rows_per_launch": rows_per_step // world,
                      "hbm_sanity_gbs": (B * D * slot_bytes) / (ms_per_step * 1e-3) / 1e9,
