@@ -137,6 +137,10 @@ UMNN_API int umnn_cc_forward(const umnn_desc* desc, const float* x0, const float
  * Replaces ParallelNeuralIntegral.backward models/UMNN/ParallelNeuralIntegral.py:110-123,
  * integrate(compute_grad=True) :66-80, computeIntegrand :83-94 (and NeuralIntegral.py:47-64,69-75,90-99).
  *   d_params [P] is OVERWRITTEN (not accumulated); any of d_x0, d_x, d_h, d_params may be NULL.
+ * This build runs the backward in FP32: desc.precision must be UMNN_PREC_FP32 and params_packed must have
+ * been packed with that precision; workspace must hold umnn_workspace_bytes(desc, 1) bytes (an L2-sized
+ * scratch for the weight-gradient operand panels; the batch is processed in chunks of whole slots).
+ * Deterministic (fixed reduction order).
  */
 UMNN_API int umnn_cc_backward(const umnn_desc* desc, const float* x0, const float* x, const float* h,
                      const void* params_packed, const float* nodes, const float* weights,

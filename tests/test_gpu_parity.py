@@ -248,6 +248,94 @@ def test_native_errors_surface_as_exceptions():
         cc_integrate(net, None, x, torch.randn(4, 6, device=_dev()), 5000)         # Q out of range
 
 
+# ---- fused backward (umnn_cc_backward) ---------------------------------------------------------------
+def _oracle_backward_with_jac(spec, flat, inp, grad_fx):
+    """Oracle gradients of  sum(integral * g) + sum(f(x,h) * grad_fx)  (float64 arithmetic)."""
+    f64 = lambda a: a.astype(np.float64)
+    x0, x, h, g = f64(inp["x0"]), f64(inp["x"]), f64(inp["h"]), f64(inp["grad_out"])
+    flat64 = f64(flat)
+    d_x0, d_x, d_flat, d_h = orc.integral_backward(spec, flat64, x0, x, h, g, inp["Q"], inp["layout"])
+    if grad_fx is not None:
+        if inp["layout"] == "strided":
+            rows = orc.slot_inputs_strided(x, h)
+        else:
+            rows = np.concatenate([x, h], axis=1)
+        gp, d_rows = orc.mlp_rows_vjp(spec, flat64, rows, f64(grad_fx).reshape(-1))
+        d_flat = d_flat + gp
+        B, Dx = x.shape
+        E = spec.widths[0] - 1
+        d_x = d_x + d_rows[:, 0].reshape(B, Dx)
+        if inp["layout"] == "strided":
+            d_h = d_h + d_rows[:, 1:].reshape(B, Dx, E).transpose(0, 2, 1).reshape(B, E * Dx)
+        else:
+            d_h = d_h + d_rows[:, 1:]
+    return d_x0, d_x, d_flat, d_h
+
+
+@pytest.mark.parametrize("with_jac", [False, True])
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_native_backward_matches_oracle(name, with_jac):
+    from umnn_b200 import kernel
+    spec, flat, inp, g = load_golden_case(name)
+    net = _net_for(spec, flat, inp["layout"], inp["Dx"])
+    kspec = net.kernel_spec()
+    d = _dev()
+    grad_fx = np.random.RandomState(5).standard_normal(inp["x"].shape).astype(np.float32) if with_jac else None
+    x0, x, h, go = (torch.from_numpy(inp[k]).to(d) for k in ("x0", "x", "h", "grad_out"))
+    assert kernel.backward_supported(kspec, x, inp["Q"])
+    d_x0, d_x, d_flat, d_h = kernel.cc_backward(kspec, x0, x, h, go, inp["Q"],
+                                                grad_fx=None if grad_fx is None else torch.from_numpy(grad_fx).to(d))
+    torch.cuda.synchronize()
+    r_x0, r_x, r_flat, r_h = _oracle_backward_with_jac(spec, flat, inp, grad_fx)
+    assert rel_to_max(d_x0.cpu().numpy(), r_x0) < 1e-5
+    assert rel_to_max(d_x.cpu().numpy(), r_x) < (GRAD_TOL if with_jac else 1e-5)
+    assert rel_to_max(d_h.cpu().numpy(), r_h) < GRAD_TOL
+    assert rel_to_max(d_flat.cpu().numpy(), r_flat) < GRAD_TOL
+    if not with_jac:
+        stride = int(g["meta_dflat_stride"])
+        assert rel_to_max(d_flat.cpu().numpy()[::stride], g["par_dflat"]) < GRAD_TOL
+        assert rel_to_max(d_h.cpu().numpy(), g["par_dh"]) < GRAD_TOL
+    # deterministic, and partial outputs may be skipped
+    again = kernel.cc_backward(kspec, x0, x, h, go, inp["Q"],
+                               grad_fx=None if grad_fx is None else torch.from_numpy(grad_fx).to(d))
+    assert torch.equal(again[2], d_flat) and torch.equal(again[3], d_h)
+    only_h = kernel.cc_backward(kspec, x0, x, h, go, inp["Q"], need_x0=False, need_x=False, need_params=False)
+    assert only_h[0] is None and only_h[2] is None and torch.equal(only_h[3], kernel.cc_backward(
+        kspec, x0, x, h, go, inp["Q"])[3])
+
+
+@pytest.mark.parametrize("B,D,E,hidden,Q,layout", [
+    (3000, 6, 30, [200, 200, 200], 50, "strided"),      # several chunks of the scratch, straddling slots
+    (257, 3, 4, [24, 16], 200, "strided"),              # slots longer than three tiles
+    (1, 1, 0, [8], 1, "contig"),                        # tiny everything, no context
+    (50, 1, 255, [256, 256], 7, "contig"),              # widest input / hidden layers
+])
+def test_native_backward_shapes(B, D, E, hidden, Q, layout):
+    from umnn_b200 import kernel
+    spec = orc.MLPSpec(tuple([1 + E] + hidden + [1]), orc.HIDDEN_LEAKY if layout == "strided" else orc.HIDDEN_RELU)
+    flat = orc.synth_params(spec, 3, 1.5)
+    Hh = E * D if layout == "strided" else E
+    x0, x, h, go = orc.synth_inputs(B, D, Hh, 4, x0_zero=False)
+    net = _net_for(spec, flat, layout, D)
+    kspec = net.kernel_spec()
+    d = _dev()
+    xd = torch.from_numpy(x).to(d)
+    if not kernel.backward_supported(kspec, xd, Q):
+        pytest.skip("shape beyond the fused backward's shared-memory budget")
+    got = kernel.cc_backward(kspec, torch.from_numpy(x0).to(d), xd, torch.from_numpy(h).to(d), torch.from_numpy(go).to(d), Q)
+    n_chk = min(B, 40)
+    inp = dict(x0=x0[:n_chk], x=x[:n_chk], h=h[:n_chk], grad_out=go[:n_chk], Q=Q, layout=layout)
+    r_x0, r_x, _, r_h = _oracle_backward_with_jac(spec, flat, inp, None)
+    assert rel_to_max(got[0][:n_chk].cpu().numpy(), r_x0) < 1e-5
+    assert rel_to_max(got[1][:n_chk].cpu().numpy(), r_x) < 1e-5
+    assert rel_to_max(got[3][:n_chk].cpu().numpy(), r_h) < GRAD_TOL
+    # parameter gradient: the same batch through the torch route on the device
+    from umnn_b200.integral import _integrate_grads_chunked
+    ref_flat, _ = _integrate_grads_chunked(torch.from_numpy(x0).to(d), xd, net, torch.from_numpy(h).to(d), Q,
+                                           torch.from_numpy(go).to(d), False)
+    assert rel_to_max(got[2].cpu().numpy(), ref_flat.cpu().numpy()) < GRAD_TOL
+
+
 # ---- full-size configurations (BASELINE.json): sampled oracle checks + size-independent properties ----
 def _full_size_check(B, D, E, hidden, Q, n_check, seed):
     from umnn_b200 import IntegrandNetwork, cc_integrate

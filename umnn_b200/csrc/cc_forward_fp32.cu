@@ -264,6 +264,12 @@ __global__ void pack_fp32_kernel(const float* __restrict__ flat, float* __restri
             if (j < L.nout[l]) v = flat[L.src_b_off[l] + j];
             break;
         }
+        if (!last && i >= L.d_off[l] && i < L.d_off[l] + L.n16[l] * L.k8[l]) {
+            const int r = i - L.d_off[l];
+            const int n = r / L.k8[l], k = r % L.k8[l];
+            if (n < L.nout[l] && k < L.nin[l]) v = flat[L.src_w_off[l] + n * L.nin[l] + k];
+            break;
+        }
     }
     packed[i] = v;
 }

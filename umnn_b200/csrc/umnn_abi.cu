@@ -159,8 +159,12 @@ int umnn_pack_params(const umnn_desc* d, const float* flat_params, void* params_
 
 size_t umnn_workspace_bytes(const umnn_desc* d, int32_t for_backward) {
     if (validate_desc(d) != 0) return 0;
-    (void)for_backward;
-    return 0;
+    if (!for_backward) return 0;
+    if (backward_fp32_unsupported_reason(d)) {
+        set_error("umnn_workspace_bytes: backward unavailable for this shape (%s)", backward_fp32_unsupported_reason(d));
+        return 0;
+    }
+    return backward_fp32_workspace_bytes(d);
 }
 
 int umnn_cc_forward(const umnn_desc* d, const float* x0, const float* x, const float* h, const void* params_packed,
@@ -193,10 +197,20 @@ int umnn_cc_backward(const umnn_desc* d, const float* x0, const float* x, const 
                      void* stream) {
     int rc = validate_desc(d);
     if (rc) return rc;
-    (void)x0; (void)x; (void)h; (void)params_packed; (void)nodes; (void)weights; (void)grad_out; (void)grad_f_at_x;
-    (void)d_x0; (void)d_x; (void)d_h; (void)d_params; (void)workspace; (void)workspace_bytes; (void)stream;
-    set_error("umnn_cc_backward: not built yet");
-    return UMNN_ERR_UNSUPPORTED;
+    if (d->precision != UMNN_PREC_FP32) {
+        set_error("umnn_cc_backward: this build runs the backward in FP32; pass desc.precision = UMNN_PREC_FP32 and "
+                  "parameters packed with that precision");
+        return UMNN_ERR_UNSUPPORTED;
+    }
+    if (d->n_samples == 0) {
+        if (d_params) UMNN_CUDA_TRY(cudaMemsetAsync(d_params, 0, sizeof(float) * (size_t)umnn_param_count(d), (cudaStream_t)stream));
+        return 0;
+    }
+    if (!x || !params_packed || !nodes || !weights || !grad_out || (d->n_ctx > 0 && !h)) {
+        set_error("umnn_cc_backward: required pointer is NULL"); return UMNN_ERR_NULL;
+    }
+    return launch_backward_fp32(d, x0, x, h, (const float*)params_packed, nodes, weights, grad_out, grad_f_at_x, d_x0, d_x,
+                                d_h, d_params, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int umnn_cc_forward_host(const umnn_desc* d, const float* x0_host, const float* x_host, const float* h_host,

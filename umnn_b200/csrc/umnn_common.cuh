@@ -41,6 +41,9 @@ struct Fp32Layout {
     int nin[UMNN_MAX_LAYERS], nout[UMNN_MAX_LAYERS], kpad[UMNN_MAX_LAYERS], npad[UMNN_MAX_LAYERS];
     int w_off[UMNN_MAX_LAYERS], b_off[UMNN_MAX_LAYERS];  // in floats
     int src_w_off[UMNN_MAX_LAYERS], src_b_off[UMNN_MAX_LAYERS];  // offsets into the flat vector
+    // backward (dgrad) copies of the hidden layers: Wd_l[n16][k8] = W_l[n][k] (untransposed), zero padded
+    // to n16 = round_up(n_out, 16) rows and k8 = round_up(n_in, 8) columns
+    int d_off[UMNN_MAX_LAYERS], n16[UMNN_MAX_LAYERS], k8[UMNN_MAX_LAYERS];
     int total_floats;
     int max_kpad;   // rows of the activation buffer
     int max_npad;   // widest padded hidden layer
@@ -76,6 +79,12 @@ inline Fp32Layout make_fp32_layout(const umnn_desc* d) {
             L.b_off[l] = off;
             off += 4;
         }
+    }
+    for (int l = 0; l < d->n_layers - 1; ++l) {
+        L.n16[l] = round_up(L.nout[l], kFp32KChunk);
+        L.k8[l] = round_up(L.nin[l], kFp32UnitsPerThread);
+        L.d_off[l] = off;
+        off += L.n16[l] * L.k8[l];
     }
     L.total_floats = off;
     return L;
@@ -120,4 +129,11 @@ int launch_pack_fp32(const umnn_desc* d, const float* flat, float* packed, cudaS
 int launch_forward_fp32(const umnn_desc* d, const float* x0, const float* x, const float* h, const float* packed,
                         const float* nodes, const float* weights, float* out, float* out_fx, float* out_fx0,
                         cudaStream_t s);
+// fused FP32 backward (cc_backward_fp32.cu)
+size_t backward_fp32_workspace_bytes(const umnn_desc* d);
+const char* backward_fp32_unsupported_reason(const umnn_desc* d);
+int launch_backward_fp32(const umnn_desc* d, const float* x0, const float* x, const float* h, const float* packed,
+                         const float* nodes, const float* weights, const float* grad_out, const float* grad_fx,
+                         float* d_x0, float* d_x, float* d_h, float* d_params, void* workspace, size_t workspace_bytes,
+                         cudaStream_t s);
 }  // namespace umnn

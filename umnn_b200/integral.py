@@ -213,7 +213,12 @@ def _forward_common(ctx, x0, x, integrand, h, nb_steps, inv_f, parallel):
     with torch.no_grad():
         if spec is not None:
             need = ctx.needs_input_grad
-            out, fx, fx0 = kernel.cc_forward(spec, x0, x, h, nb_steps, want_fx=bool(need[1]), want_fx0=bool(need[0]))
+            # the fused backward re-evaluates f(x), f(x0) itself; only when it cannot serve the shape are
+            # the Leibniz terms taken from extra rows of the forward launch
+            ctx.native_bwd = any(need) and kernel.backward_supported(spec, x, nb_steps)
+            want_fx = bool(need[1]) and not ctx.native_bwd
+            want_fx0 = bool(need[0]) and not ctx.native_bwd
+            out, fx, fx0 = kernel.cc_forward(spec, x0, x, h, nb_steps, want_fx=want_fx, want_fx0=want_fx0)
             ctx.has_fx, ctx.has_fx0 = fx is not None, fx0 is not None
             extra = [t for t in (fx, fx0) if t is not None]
             ctx.save_for_backward(x0.clone(), x.clone(), h, *extra)
@@ -231,6 +236,11 @@ def _backward_common(ctx, grad_output, parallel):
     x0, x, h = saved[0], saved[1], saved[2]
     integrand, nb_steps, inv_f, spec = ctx.integrand, ctx.nb_steps, ctx.inv_f, ctx.kernel_spec
     need = ctx.needs_input_grad
+    if spec is not None and ctx.native_bwd:
+        d_x0, d_x, d_flat, d_h = kernel.cc_backward(spec, x0, x, h, grad_output, nb_steps, need_x0=bool(need[0]),
+                                                    need_x=bool(need[1]), need_h=bool(need[4]),
+                                                    need_params=bool(need[3]))
+        return d_x0, d_x, d_flat, d_h
     if spec is not None:
         grad_output = grad_output.contiguous()
         extra = list(saved[3:])
@@ -240,8 +250,8 @@ def _backward_common(ctx, grad_output, parallel):
         d_x0 = -fx0 * grad_output if fx0 is not None else None
         d_flat = d_h = None
         if need[3] or need[4]:
-            # parameter / context gradients: torch ops on the same CUDA device, batch-chunked, until
-            # umnn_cc_backward (the fused backward kernel) serves them
+            # shapes the fused backward cannot hold in shared memory: torch ops on the same CUDA device,
+            # batch-chunked
             d_flat, d_h = _integrate_grads_chunked(x0, x, integrand, h, nb_steps, grad_output, False)
             d_h = d_h.view(h.shape)
             if not need[3]:

@@ -46,7 +46,7 @@ def packed_parameters(spec: KernelSpec, desc: _native.Desc, device: torch.device
     stamp = None
     if not owner.training:
         stamp = (desc.precision, str(device)) + tuple((id(p), p.data_ptr(), p._version) for p in spec.parameters())
-        hit = owner.__dict__.get("_umnn_packed")
+        hit = owner.__dict__.get("_umnn_packed", {}).get(desc.precision)
         if hit is not None and hit[0] == stamp:
             return hit[1]
     nbytes = L.umnn_packed_params_bytes(desc)
@@ -59,7 +59,7 @@ def packed_parameters(spec: KernelSpec, desc: _native.Desc, device: torch.device
     with torch.cuda.device(device):
         _native.check(L.umnn_pack_params(desc, flat.data_ptr(), packed.data_ptr(), stream))
     if stamp is not None:
-        owner.__dict__["_umnn_packed"] = (stamp, packed)
+        owner.__dict__.setdefault("_umnn_packed", {})[desc.precision] = (stamp, packed)
     else:
         owner.__dict__.pop("_umnn_packed", None)
     return packed
@@ -135,3 +135,50 @@ def cc_forward_host(spec_widths, layout, hidden_act, out_act, flat_params, x0, x
                                          out.ctypes.data, None if fx is None else fx.ctypes.data,
                                          None if fx0 is None else fx0.ctypes.data, device))
     return out, fx, fx0
+
+
+def backward_supported(spec: KernelSpec, x: torch.Tensor, nb_steps: int) -> bool:
+    """True if umnn_cc_backward (fused FP32 backward) can serve this shape."""
+    L = _native.lib()
+    desc = make_desc(spec, x, nb_steps, _native.PREC_FP32)
+    return L.umnn_workspace_bytes(desc, 1) > 0 or x.shape[0] == 0
+
+
+def cc_backward(spec: KernelSpec, x0: Optional[torch.Tensor], x: torch.Tensor, h: torch.Tensor,
+                grad_out: torch.Tensor, nb_steps: int, grad_fx: Optional[torch.Tensor] = None,
+                need_x0: bool = True, need_x: bool = True, need_h: bool = True, need_params: bool = True):
+    """Fused backward through the C ABI: (d_x0, d_x, d_flat_params, d_h); entries not requested are None.
+
+    Replaces ParallelNeuralIntegral.backward / integrate(compute_grad=True) / computeIntegrand of the
+    reference (see include/umnn_b200.h).  `grad_fx` is an optional cotangent of f(x, h) (the Jacobian point).
+    """
+    L = _native.lib()
+    x = _as_f32c(x)
+    h = _as_f32c(h)
+    grad_out = _as_f32c(grad_out)
+    x0 = None if x0 is None else _as_f32c(x0)
+    grad_fx = None if grad_fx is None else _as_f32c(grad_fx)
+    desc = make_desc(spec, x, nb_steps, _native.PREC_FP32)
+    dev = x.device
+    d_x0 = torch.empty_like(x) if need_x0 else None
+    d_x = torch.empty_like(x) if need_x else None
+    d_h = torch.empty_like(h) if need_h else None
+    n_params = int(L.umnn_param_count(desc))
+    d_flat = torch.empty(n_params, dtype=torch.float32, device=dev) if need_params else None
+    if x.shape[0] == 0:
+        if d_flat is not None:
+            d_flat.zero_()
+        return d_x0, d_x, d_flat, d_h
+    packed = packed_parameters(spec, desc, dev)
+    w, t = device_tables(nb_steps, dev)
+    ws_bytes = L.umnn_workspace_bytes(desc, 1)
+    if ws_bytes == 0:
+        msg = L.umnn_last_error()
+        raise _native.NativeError(_native_err_unsupported, msg.decode("utf-8", "replace") if msg else "")
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        _native.check(L.umnn_cc_backward(desc, _ptr(x0), x.data_ptr(), h.data_ptr(), packed.data_ptr(), t.data_ptr(),
+                                         w.data_ptr(), grad_out.data_ptr(), _ptr(grad_fx), _ptr(d_x0), _ptr(d_x),
+                                         _ptr(d_h), _ptr(d_flat), ws.data_ptr(), ws_bytes, stream))
+    return d_x0, d_x, d_flat, d_h
