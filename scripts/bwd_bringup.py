@@ -7,8 +7,11 @@ from oracle import umnn_oracle as orc
 from umnn_b200 import IntegrandNetwork, kernel
 from umnn_b200.integral import _integrate_grads_chunked
 
-for (B, D, E, hidden, Q) in [(1000, 6, 30, [200, 200, 200], 50), (10000, 6, 30, [200, 200, 200], 50),
-                             (10000, 2, 10, [100] * 4, 50), (100, 784, 30, [100, 50, 50, 50, 50], 50)]:
+CASES = [(1000, 6, 30, [200, 200, 200], 50), (10000, 6, 30, [200, 200, 200], 50),
+         (10000, 2, 10, [100] * 4, 50), (100, 784, 30, [100, 50, 50, 50, 50], 50)]
+if len(sys.argv) > 1:
+    CASES = [CASES[int(sys.argv[1])]]
+for (B, D, E, hidden, Q) in CASES:
     spec = orc.MLPSpec(tuple([1 + E] + hidden + [1]))
     flat = orc.synth_params(spec, 0)
     x0, x, h, g = orc.synth_inputs(B, D, E * D, 1)
@@ -30,7 +33,7 @@ for (B, D, E, hidden, Q) in [(1000, 6, 30, [200, 200, 200], 50), (10000, 6, 30, 
         for _ in range(reps): out = fn()
         e.record(); torch.cuda.synchronize()
         res[name] = (s.elapsed_time(e) / reps, out)
-    dflat_n, dflat_t = res["native"][1][2], res["torch"][1][0]
+    dflat_n, dflat_t = res["native"][1][2], res["torch"][1][0].detach()
     err = float((dflat_n - dflat_t).abs().max() / dflat_t.abs().max())
     print(f"B={B} D={D} hidden={hidden}: native {res['native'][0]:.2f} ms, torch route {res['torch'][0]:.2f} ms, "
           f"speedup {res['torch'][0] / res['native'][0]:.2f}x, dflat rel-to-max diff {err:.2e}", flush=True)

@@ -24,7 +24,7 @@ constexpr int kRG = 16;   // thread columns: 4 rows each
 constexpr int kKC = kFp32KChunk;
 constexpr int kUT = kFp32UnitsPerThread;
 constexpr long long kChunkRowsTarget = 49152;
-constexpr int kMaxSplit = 16;
+constexpr int kMaxSplit = 64;
 
 struct BwdParams {
     const float *x0, *x, *h, *packed, *nodes, *weights, *grad_out, *grad_fx;
@@ -321,86 +321,110 @@ __global__ void __launch_bounds__(512) cc_backward_fp32_kernel(const BwdParams p
 // ---------------------------------------------------------------------------------------------
 // weight gradient: C[n][k] = sum_r DZ[n][r] * A[k][r]  (k == nin: bias, A == 1), split over row slabs
 // ---------------------------------------------------------------------------------------------
-constexpr int kWT = 64;   // output tile
-constexpr int kWK = 32;   // rows per smem step
+constexpr int kWT = 128;  // output tile (n and k)
+constexpr int kWK = 16;   // rows per shared-memory step
 constexpr int kWP = kWT + 4;
 
+// 256 threads, 8 x 8 outputs each (n: tn*4..+3 and 64+tn*4..+3, k likewise) so every smem read is a
+// conflict-free float4; operands are transposed on the way in ([dim][rows] panels -> [r][dim] tiles)
 __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ dz, const float* __restrict__ a, long long ld,
                                                     long long rows, long long slab, int nout, int nin, float* __restrict__ part,
                                                     long long part_stride, int w_dst, int b_dst) {
-    __shared__ __align__(16) float As[kWK][kWP];   // [r][n]
-    __shared__ __align__(16) float Bs[kWK][kWP];   // [r][k]
+    __shared__ __align__(16) float As[2][kWK][kWP];   // [stage][r][n]
+    __shared__ __align__(16) float Bs[2][kWK][kWP];   // [stage][r][k]
     const int tid = threadIdx.x;
     const int k0 = blockIdx.x * kWT, n0 = blockIdx.y * kWT;
     const long long r_begin = (long long)blockIdx.z * slab;
     long long r_end = r_begin + slab;
     if (r_end > rows) r_end = rows;
     const int tn = (tid >> 4) * 4, tk = (tid & 15) * 4;
-    float acc[4][4];
+    float acc[8][8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
 
-    for (long long r0 = r_begin; r0 < r_end; r0 += kWK) {
-        // 64 x 32 elements per operand, 256 threads: 8 elements each (two float4 along r)
+    // each thread moves 2 float4 (along r) per operand per step: 128 dims x 16 rows = 512 float4
+    auto load_tile = [&](long long r0, float4 (&va)[2], float4 (&vb)[2]) {
+#pragma unroll
         for (int it = 0; it < 2; ++it) {
-            const int e = tid + it * 256;          // 0..511
-            const int row_in_tile = e >> 3;        // 0..63  (n or k index inside the tile)
-            const int r4 = (e & 7) * 4;            // 0..28
-            const long long r = r0 + r4;
-            float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
-            const int n = n0 + row_in_tile, k = k0 + row_in_tile;
+            const int e = tid + it * 256;
+            const int dim = e >> 2;              // 0..127
+            const long long r = r0 + (e & 3) * 4;
+            va[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            vb[it] = va[it];
+            const int n = n0 + dim, k = k0 + dim;
             if (n < nout) {
                 const float* src = dz + (size_t)n * ld + r;
-                if (r + 3 < r_end) va = *reinterpret_cast<const float4*>(src);
+                if (r + 3 < r_end) va[it] = *reinterpret_cast<const float4*>(src);
                 else {
-                    if (r < r_end) va.x = src[0];
-                    if (r + 1 < r_end) va.y = src[1];
-                    if (r + 2 < r_end) va.z = src[2];
+                    if (r < r_end) va[it].x = src[0];
+                    if (r + 1 < r_end) va[it].y = src[1];
+                    if (r + 2 < r_end) va[it].z = src[2];
                 }
             }
             if (k < nin) {
                 const float* src = a + (size_t)k * ld + r;
-                if (r + 3 < r_end) vb = *reinterpret_cast<const float4*>(src);
+                if (r + 3 < r_end) vb[it] = *reinterpret_cast<const float4*>(src);
                 else {
-                    if (r < r_end) vb.x = src[0];
-                    if (r + 1 < r_end) vb.y = src[1];
-                    if (r + 2 < r_end) vb.z = src[2];
+                    if (r < r_end) vb[it].x = src[0];
+                    if (r + 1 < r_end) vb[it].y = src[1];
+                    if (r + 2 < r_end) vb[it].z = src[2];
                 }
             } else if (k == nin) {   // bias column: A == 1 on valid rows
-                vb.x = (r < r_end) ? 1.f : 0.f;
-                vb.y = (r + 1 < r_end) ? 1.f : 0.f;
-                vb.z = (r + 2 < r_end) ? 1.f : 0.f;
-                vb.w = (r + 3 < r_end) ? 1.f : 0.f;
+                vb[it].x = (r < r_end) ? 1.f : 0.f;
+                vb[it].y = (r + 1 < r_end) ? 1.f : 0.f;
+                vb[it].z = (r + 2 < r_end) ? 1.f : 0.f;
+                vb[it].w = (r + 3 < r_end) ? 1.f : 0.f;
             }
-            As[r4 + 0][row_in_tile] = va.x; As[r4 + 1][row_in_tile] = va.y;
-            As[r4 + 2][row_in_tile] = va.z; As[r4 + 3][row_in_tile] = va.w;
-            Bs[r4 + 0][row_in_tile] = vb.x; Bs[r4 + 1][row_in_tile] = vb.y;
-            Bs[r4 + 2][row_in_tile] = vb.z; Bs[r4 + 3][row_in_tile] = vb.w;
         }
-        __syncthreads();
-#pragma unroll 8
+    };
+    auto store_tile = [&](int stage, const float4 (&va)[2], const float4 (&vb)[2]) {
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int e = tid + it * 256;
+            const int dim = e >> 2, r4 = (e & 3) * 4;
+            As[stage][r4 + 0][dim] = va[it].x; As[stage][r4 + 1][dim] = va[it].y;
+            As[stage][r4 + 2][dim] = va[it].z; As[stage][r4 + 3][dim] = va[it].w;
+            Bs[stage][r4 + 0][dim] = vb[it].x; Bs[stage][r4 + 1][dim] = vb[it].y;
+            Bs[stage][r4 + 2][dim] = vb[it].z; Bs[stage][r4 + 3][dim] = vb[it].w;
+        }
+    };
+
+    float4 va[2], vb[2];
+    if (r_begin < r_end) {
+        load_tile(r_begin, va, vb);
+        store_tile(0, va, vb);
+    }
+    __syncthreads();
+    int stage = 0;
+    for (long long r0 = r_begin; r0 < r_end; r0 += kWK, stage ^= 1) {
+        const bool more = r0 + kWK < r_end;
+        if (more) load_tile(r0 + kWK, va, vb);      // global loads in flight during the FMAs below
+#pragma unroll
         for (int r = 0; r < kWK; ++r) {
-            const float4 x = *reinterpret_cast<const float4*>(&As[r][tn]);
-            const float4 y = *reinterpret_cast<const float4*>(&Bs[r][tk]);
-            const float xa[4] = {x.x, x.y, x.z, x.w};
-            const float ya[4] = {y.x, y.y, y.z, y.w};
+            const float4 x0 = *reinterpret_cast<const float4*>(&As[stage][r][tn]);
+            const float4 x1 = *reinterpret_cast<const float4*>(&As[stage][r][64 + tn]);
+            const float4 y0 = *reinterpret_cast<const float4*>(&Bs[stage][r][tk]);
+            const float4 y1 = *reinterpret_cast<const float4*>(&Bs[stage][r][64 + tk]);
+            const float xa[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+            const float ya[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xa[i], ya[j], acc[i][j]);
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xa[i], ya[j], acc[i][j]);
         }
+        if (more) store_tile(stage ^ 1, va, vb);
         __syncthreads();
     }
     float* out = part + (size_t)blockIdx.z * part_stride;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int n = n0 + tn + i;
+    for (int i = 0; i < 8; ++i) {
+        const int n = n0 + (i < 4 ? tn + i : 64 + tn + i - 4);
         if (n >= nout) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int k = k0 + tk + j;
+        for (int j = 0; j < 8; ++j) {
+            const int k = k0 + (j < 4 ? tk + j : 64 + tk + j - 4);
             if (k < nin) out[w_dst + (size_t)n * nin + k] = acc[i][j];
             else if (k == nin) out[b_dst + n] = acc[i][j];
         }
@@ -440,8 +464,19 @@ bool make_plan(const umnn_desc* d, BwdPlan* B) {
     }
     B->rps = d->nb_steps + 3;
     const long long n_slots = d->n_samples * (long long)d->n_dims;
-    long long cs = kChunkRowsTarget / B->rps;
-    if (cs < 1) cs = 1;
+    // a chunk = n_cta x s whole slots, s chosen so that s*rps fills its 64-row tiles with the least padding
+    const int n_cta = 148;
+    const long long per_cta_target = kChunkRowsTarget / n_cta;
+    long long s_max = per_cta_target / B->rps;
+    if (s_max < 1) s_max = 1;
+    long long best_s = s_max;
+    double best_waste = 2.0;
+    for (long long sc = s_max; sc >= 1 && sc * 2 >= s_max; --sc) {
+        const long long rows_c = sc * B->rps;
+        const double waste = (double)((rows_c + kTR - 1) / kTR * kTR - rows_c) / (double)rows_c;
+        if (waste < best_waste - 1e-9) { best_waste = waste; best_s = sc; }
+    }
+    long long cs = best_s * n_cta;
     if (cs > n_slots) cs = n_slots > 0 ? n_slots : 1;
     B->chunk_slots = cs;
     B->chunk_rows = cs * B->rps;
@@ -538,7 +573,7 @@ int launch_backward_fp32(const umnn_desc* d, const float* x0, const float* x, co
         cc_backward_fp32_kernel<<<(unsigned)grid, B.threads, B.smem, s>>>(p);
         UMNN_CUDA_TRY(cudaGetLastError());
         if (d_params) {
-            int nsplit = (int)((rows + 4095) / 4096);
+            int nsplit = (int)((rows + 1023) / 1024);
             if (nsplit > kMaxSplit) nsplit = kMaxSplit;
             if (nsplit < 1) nsplit = 1;
             long long slab = (rows + nsplit - 1) / nsplit;

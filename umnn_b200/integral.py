@@ -215,7 +215,8 @@ def _forward_common(ctx, x0, x, integrand, h, nb_steps, inv_f, parallel):
             need = ctx.needs_input_grad
             # the fused backward re-evaluates f(x), f(x0) itself; only when it cannot serve the shape are
             # the Leibniz terms taken from extra rows of the forward launch
-            ctx.native_bwd = any(need) and kernel.backward_supported(spec, x, nb_steps)
+            ctx.native_bwd = (any(need) and os.environ.get("UMNN_B200_BACKWARD", "native") != "torch"
+                              and kernel.backward_supported(spec, x, nb_steps))
             want_fx = bool(need[1]) and not ctx.native_bwd
             want_fx0 = bool(need[0]) and not ctx.native_bwd
             out, fx, fx0 = kernel.cc_forward(spec, x0, x, h, nb_steps, want_fx=want_fx, want_fx0=want_fx0)
