@@ -137,10 +137,12 @@ UMNN_API int umnn_cc_forward(const umnn_desc* desc, const float* x0, const float
  * Replaces ParallelNeuralIntegral.backward models/UMNN/ParallelNeuralIntegral.py:110-123,
  * integrate(compute_grad=True) :66-80, computeIntegrand :83-94 (and NeuralIntegral.py:47-64,69-75,90-99).
  *   d_params [P] is OVERWRITTEN (not accumulated); any of d_x0, d_x, d_h, d_params may be NULL.
- * This build runs the backward in FP32: desc.precision must be UMNN_PREC_FP32 and params_packed must have
- * been packed with that precision; workspace must hold umnn_workspace_bytes(desc, 1) bytes (an L2-sized
- * scratch for the weight-gradient operand panels; the batch is processed in chunks of whole slots).
- * Deterministic (fixed reduction order).
+ * desc.precision selects the path (and must be the precision params_packed was packed with):
+ * UMNN_PREC_BF16X3 / AUTO = three tensor-core passes per chunk of rows (forward re-evaluation with operand
+ * emission, dgrad with transposed weights, split-K weight-gradient GEMM), UMNN_PREC_FP32 = fused FFMA kernel
+ * + FFMA split-K GEMM.  workspace must hold umnn_workspace_bytes(desc, 1) bytes (operand panels of one chunk;
+ * the batch is processed in chunks of whole slots).  A shape the tensor-core backward cannot serve returns
+ * UMNN_ERR_UNSUPPORTED (retry with UMNN_PREC_FP32).  Deterministic (fixed reduction order).
  */
 UMNN_API int umnn_cc_backward(const umnn_desc* desc, const float* x0, const float* x, const float* h,
                      const void* params_packed, const float* nodes, const float* weights,

@@ -22,6 +22,8 @@
 // warp 19 MMA issuer (one elected lane of the leader CTA).
 #include "tc_common.cuh"
 #include "tc_layout.cuh"
+#include "tc_bwd_layout.cuh"
+#include "tc_kernels.cuh"
 
 #include <stdlib.h>
 
@@ -50,24 +52,6 @@ constexpr int BAR_PEER = BAR_WLOAD + 1;
 constexpr int BAR_COUNT = BAR_PEER + 1;
 static_assert(BAR_COUNT <= kTcNumBars, "barrier table too small");
 
-struct TcParams {
-    const float* x0;
-    const float* x;
-    const float* h;
-    const float* nodes;
-    const float* weights;
-    const uint8_t* blobs;  // [2][blob_bytes]
-    float* out;
-    float* out_fx;
-    float* out_fx0;
-    long long n_slots;
-    long long slots_per_cta;
-    int tiles_per_cta;
-    int D, E, layout, Q, rps, out_act;
-    TcLayout L;
-    TcSmem S;
-};
-
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
@@ -93,7 +77,16 @@ __device__ __forceinline__ float hact(float v) {
     return HIDDEN_ACT == UMNN_ACT_LEAKY_RELU ? fmaxf(v, v * kLeakySlope) : fmaxf(v, 0.0f);
 }
 
-template <int HIDDEN_ACT>
+// two 16-byte granules (16 columns) of a bf16 hi / lo panel pair: o[0..7] = hi pairs, o[8..15] = lo pairs
+__device__ __forceinline__ void emit16(uint8_t* hi, uint8_t* lo, long long pr, int col, int W, const uint32_t (&o)[16]) {
+    const size_t g0 = panel_offset(pr, col, W), g1 = panel_offset(pr, col + 8, W);
+    *reinterpret_cast<uint4*>(hi + g0) = make_uint4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<uint4*>(hi + g1) = make_uint4(o[4], o[5], o[6], o[7]);
+    *reinterpret_cast<uint4*>(lo + g0) = make_uint4(o[8], o[9], o[10], o[11]);
+    *reinterpret_cast<uint4*>(lo + g1) = make_uint4(o[12], o[13], o[14], o[15]);
+}
+
+template <int HIDDEN_ACT, bool EMIT>
 __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -119,9 +112,9 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
     const float* w1h = reinterpret_cast<const float*>(smem + L.off_w1h);
     const float* w4 = reinterpret_cast<const float*>(smem + L.off_w4);
 
-    const long long slot_begin = (long long)blockIdx.x * p.slots_per_cta;
+    const long long slot_begin = p.slot0 + (long long)blockIdx.x * p.slots_per_cta;
     long long slot_end = slot_begin + p.slots_per_cta;
-    if (slot_end > p.n_slots) slot_end = p.n_slots;
+    if (slot_end > p.slot0 + p.n_slots) slot_end = p.slot0 + p.n_slots;
     const long long n_rows = slot_end > slot_begin ? (slot_end - slot_begin) * p.rps : 0;
 
     // ---------------------------------------------------------------- setup
@@ -244,7 +237,7 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
                     if (node <= p.Q) {
                         const float xT = upper_limit(lo, hi, p.Q);
                         xi = node_abscissa(lo, __fsub_rn(xT, lo), tab_t[node]);
-                    } else if (node == p.Q + 1 && p.out_fx) {
+                    } else if (node == p.Q + 1 && p.x_row) {
                         xi = hi;
                     } else {
                         xi = lo;
@@ -255,6 +248,37 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
                 nodeid[b * kTcTile + r] = node;
             }
             prep_bar_sync();
+            if (EMIT) {
+                // A_0 = [x_row, h_slot, 1, 0...] as bf16 hi / lo (operand of the first layer's weight gradient)
+                const int W0 = p.emit.width[0];
+                const int n_gran = W0 / 8;
+                for (int idx = ptid; idx < kTcTile * n_gran; idx += kPrepThreads) {
+                    const int r = idx / n_gran, gidx = idx - r * n_gran;
+                    const long long pr = (long long)blockIdx.x * p.emit.row_block + row0 + r;
+                    const int node = nodeid[b * kTcTile + r];
+                    const float* hv = hbuf + lsrel[b * kTcTile + r] * p.E;
+                    uint32_t hi4[4], lo4[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float v2[2];
+#pragma unroll
+                        for (int q2 = 0; q2 < 2; ++q2) {
+                            const int c = gidx * 8 + 2 * i + q2;
+                            float val = 0.0f;
+                            if (node >= 0) {
+                                if (c == 0) val = xnode[b * kTcTile + r];
+                                else if (c <= p.E) val = hv[c - 1];
+                                else if (c == p.E + 1) val = 1.0f;
+                            }
+                            v2[q2] = val;
+                        }
+                        split_bf16x2(v2[0], v2[1], hi4[i], lo4[i]);
+                    }
+                    const size_t go = panel_offset(pr, gidx * 8, W0);
+                    *reinterpret_cast<uint4*>(p.emit.a_hi[0] + go) = make_uint4(hi4[0], hi4[1], hi4[2], hi4[3]);
+                    *reinterpret_cast<uint4*>(p.emit.a_lo[0] + go) = make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]);
+                }
+            }
             float* cv = cvec + (size_t)b * p.S.max_slots * L.npad1;
             for (int idx = ptid; idx < ns * L.npad1; idx += kPrepThreads) {
                 const int i = idx / L.npad1, n = idx - i * L.npad1;
@@ -282,19 +306,25 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
 
         mbar_wait(&bars[BAR_WLOAD], 0, 130);
 
-        // one 16-column half of layer 1 for the tile in prep buffer `bu` -> A operand of MMA layer 0 (region Q)
-        auto l1_half = [&](int bu, int c16) {
+        const long long cta_row0 = (long long)blockIdx.x * (EMIT ? p.emit.row_block : 0);
+        // one 16-column half of layer 1 for the tile `tile` (prep buffer `bu`) -> A operand of MMA layer 0
+        // (region Q); returns the sign bits of the 16 activations
+        auto l1_half = [&](int bu, int tile, int c16) -> uint32_t {
             const float xn = xnode[bu * kTcTile + r];
             const float* cv = cvec + ((size_t)bu * p.S.max_slots + lsrel[bu * kTcTile + r]) * L.npad1 + 16 * c16;
             const float* wx = w1x + 16 * c16;
             uint32_t o[16];
+            uint32_t bits = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float a0 = hact<HIDDEN_ACT>(fmaf(xn, wx[2 * i], cv[2 * i]));
                 const float a1 = hact<HIDDEN_ACT>(fmaf(xn, wx[2 * i + 1], cv[2 * i + 1]));
                 split_bf16x2(a0, a1, o[i], o[8 + i]);
+                if (EMIT) bits |= (a0 > 0.0f ? 1u : 0u) << (2 * i) | (a1 > 0.0f ? 1u : 0u) << (2 * i + 1);
             }
             tmem_st16(tbase + lane_sel + kColQ + 16u * c16, o);
+            if (EMIT) emit16(p.emit.a_hi[1], p.emit.a_lo[1], cta_row0 + (long long)tile * kTcTile + r, 16 * c16, L.npad1, o);
+            return bits;
         };
         // publish pair `pp` of MMA layer `m`'s A operand (both CTAs arrive on the leader's barrier)
         auto publish = [&](int m, int pp) {
@@ -303,15 +333,16 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(&bars[BAR_READY + m * 8 + pp], 0);
         };
-        auto l1_pair = [&](int bu, int pp) {
-            l1_half(bu, 2 * pp);
-            if (32 * pp + 16 < L.npad1) l1_half(bu, 2 * pp + 1);
+        auto l1_pair = [&](int bu, int tile, int pp) {
+            uint32_t bits = l1_half(bu, tile, 2 * pp);
+            if (32 * pp + 16 < L.npad1) bits |= l1_half(bu, tile, 2 * pp + 1) << 16;
+            if (EMIT) p.emit.mask[1][(cta_row0 + (long long)tile * kTcTile + r) * 8 + pp] = bits;
             publish(0, pp);
         };
 
         // prologue: layer 1 of tile 0
         mbar_wait(&bars[BAR_PREP_FULL + 0], 0, 131);
-        for (int pp = cg; pp < pairs1; pp += kColGroups) l1_pair(0, pp);
+        for (int pp = cg; pp < pairs1; pp += kColGroups) l1_pair(0, 0, pp);
 
         for (int t = 0; t < T; ++t) {
             const uint32_t par = (uint32_t)(t & 1);
@@ -334,18 +365,27 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
                     tmem_ld16(taddr, v0);
                     if (two) tmem_ld16(taddr + 16, v1);
                     tmem_ld_wait();
+                    const long long pr = cta_row0 + (long long)t * kTcTile + r;
+                    uint32_t bits = 0;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        split_bf16x2(hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i + 1])),
-                                     o[i], o[8 + i]);
+                    for (int i = 0; i < 8; ++i) {
+                        const float a0 = hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i])), a1 = hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i + 1]));
+                        split_bf16x2(a0, a1, o[i], o[8 + i]);
+                        if (EMIT) bits |= (a0 > 0.0f ? 1u : 0u) << (2 * i) | (a1 > 0.0f ? 1u : 0u) << (2 * i + 1);
+                    }
                     tmem_st16(taddr, o);
+                    if (EMIT) emit16(p.emit.a_hi[m + 2], p.emit.a_lo[m + 2], pr, 32 * pp, y.npad, o);
                     if (two) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            split_bf16x2(hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i + 1])),
-                                         o[i], o[8 + i]);
+                        for (int i = 0; i < 8; ++i) {
+                            const float a0 = hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i])), a1 = hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i + 1]));
+                            split_bf16x2(a0, a1, o[i], o[8 + i]);
+                            if (EMIT) bits |= (a0 > 0.0f ? 1u : 0u) << (16 + 2 * i) | (a1 > 0.0f ? 1u : 0u) << (17 + 2 * i);
+                        }
                         tmem_st16(taddr + 16, o);
+                        if (EMIT) emit16(p.emit.a_hi[m + 2], p.emit.a_lo[m + 2], pr, 32 * pp + 16, y.npad, o);
                     }
+                    if (EMIT) p.emit.mask[m + 2][pr * 8 + pp] = bits;
                     publish(m + 1, pp);
                 }
             }
@@ -373,12 +413,34 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
 #pragma unroll
                         for (int i = 0; i < 16; ++i) partial = fmaf(hact<HIDDEN_ACT>(__uint_as_float(v1[i])), wv[16 + i], partial);
                     }
+                    if (EMIT) {
+                        // last hidden activations a_J (operand of the output layer's weight gradient) and their signs
+                        const long long pr = cta_row0 + (long long)t * kTcTile + r;
+                        uint32_t o[16], bits = 0;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float a0 = hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i])), a1 = hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i + 1]));
+                            split_bf16x2(a0, a1, o[i], o[8 + i]);
+                            bits |= (a0 > 0.0f ? 1u : 0u) << (2 * i) | (a1 > 0.0f ? 1u : 0u) << (2 * i + 1);
+                        }
+                        emit16(p.emit.a_hi[n_mma + 1], p.emit.a_lo[n_mma + 1], pr, 32 * pp, L.npadL, o);
+                        if (two) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float a0 = hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i])), a1 = hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i + 1]));
+                                split_bf16x2(a0, a1, o[i], o[8 + i]);
+                                bits |= (a0 > 0.0f ? 1u : 0u) << (16 + 2 * i) | (a1 > 0.0f ? 1u : 0u) << (17 + 2 * i);
+                            }
+                            emit16(p.emit.a_hi[n_mma + 1], p.emit.a_lo[n_mma + 1], pr, 32 * pp + 16, L.npadL, o);
+                        }
+                        p.emit.mask[n_mma + 1][pr * 8 + pp] = bits;
+                    }
                 } else if (even_layers) {
                     // columns beyond the last accumulator: free once every MMA of this tile is done
                     for (int s = 0; s < ylast.nseg; ++s) mbar_wait(&bars[BAR_ACC + (n_mma - 1) * 2 + s], par, 320 + s);
                     tc_fence_after_sync();
                 }
-                if (even_layers && has_next && pp < pairs1) l1_pair(bn, pp);
+                if (even_layers && has_next && pp < pairs1) l1_pair(bn, t + 1, pp);
             }
 
             // ---- finalize the rows of this tile
@@ -390,24 +452,26 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
                 for (int s = 0; s < ylast.nseg; ++s) mbar_wait(&bars[BAR_ACC + (n_mma - 1) * 2 + s], par, 330 + s);
                 tc_fence_after_sync();
                 mbar_wait(&bars[BAR_PREP_FULL + bn], (uint32_t)(((t + 1) / kTcPrepBufs) & 1), 133);
-                for (int pp = cg; pp < pairs1; pp += kColGroups) l1_pair(bn, pp);
+                for (int pp = cg; pp < pairs1; pp += kColGroups) l1_pair(bn, t + 1, pp);
             }
             const long long row0 = (long long)t * kTcTile;
             if (cg == 0) {
                 const int node = nodeid[b * kTcTile + r];
+                const float vtot = ((partial + part[r]) + part[kTcTile + r]) + part[2 * kTcTile + r];
+                if (EMIT) p.emit.v[cta_row0 + row0 + r] = node >= 0 ? vtot : 0.0f;
                 if (node >= 0) {
-                    const float f = out_act(((partial + part[r]) + part[kTcTile + r]) + part[2 * kTcTile + r], p.out_act);
+                    const float f = out_act(vtot, p.out_act);
                     if (node <= p.Q) {
                         fval[r] = f * tab_w[node];
-                    } else {
+                    } else if (!EMIT) {
                         const long long slot = slot_begin + (row0 + r) / p.rps;
-                        if (node == p.Q + 1 && p.out_fx) p.out_fx[slot] = f;
+                        if (node == p.Q + 1 && p.x_row) p.out_fx[slot] = f;
                         else p.out_fx0[slot] = f;
                     }
                 }
             }
             epi_bar_sync();
-            if (warp == 0 && row0 < n_rows) {
+            if (!EMIT && warp == 0 && row0 < n_rows) {
                 const long long last_row = (row0 + kTcTile < n_rows ? row0 + kTcTile : n_rows) - 1;
                 const long long s_first = row0 / p.rps, s_last = last_row / p.rps;
                 for (long long ls = s_first; ls <= s_last; ++ls) {
@@ -579,6 +643,8 @@ int launch_forward_tc(const umnn_desc* d, const float* x0, const float* x, const
     p.n_slots = d->n_samples * (long long)d->n_dims;
     p.D = d->n_dims; p.E = d->n_ctx; p.layout = d->layout; p.Q = d->nb_steps; p.out_act = d->out_act;
     p.rps = d->nb_steps + 1 + (out_fx ? 1 : 0) + (out_fx0 ? 1 : 0);
+    p.x_row = out_fx ? 1 : 0;
+    p.slot0 = 0;
     p.S = make_tc_smem(p.L, p.rps, p.Q);
     if (p.S.total > kTcMaxSmem) {
         set_error("BF16X3: needs %u bytes of shared memory (max %zu)", p.S.total, kTcMaxSmem);
@@ -598,8 +664,8 @@ int launch_forward_tc(const umnn_desc* d, const float* x0, const float* x, const
     p.slots_per_cta = (p.n_slots + n_cta - 1) / n_cta;
     p.tiles_per_cta = (int)((p.slots_per_cta * p.rps + kTcTile - 1) / kTcTile);
 
-    auto kern = d->hidden_act == UMNN_ACT_LEAKY_RELU ? cc_forward_tc_kernel<UMNN_ACT_LEAKY_RELU>
-                                                     : cc_forward_tc_kernel<UMNN_ACT_RELU>;
+    auto kern = d->hidden_act == UMNN_ACT_LEAKY_RELU ? cc_forward_tc_kernel<UMNN_ACT_LEAKY_RELU, false>
+                                                     : cc_forward_tc_kernel<UMNN_ACT_RELU, false>;
     UMNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.S.total));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)n_cta);
@@ -616,5 +682,47 @@ int launch_forward_tc(const umnn_desc* d, const float* x0, const float* x, const
     UMNN_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
     return 0;
 }
+
+// pass F of the tensor-core backward: the forward kernel over one chunk of slots with panel emission
+int launch_forward_tc_emit(const umnn_desc* d, const float* x0, const float* x, const float* h, const void* packed,
+                           const float* nodes, const float* weights, long long slot0, long long n_slots_chunk,
+                           long long slots_per_cta, int tiles_per_cta, int n_cta, const TcEmit& emit, cudaStream_t s) {
+    TcParams p{};
+    if (!make_tc_layout(d, &p.L, tc_two_segments())) {
+        set_error("BF16X3: shape not supported by the tensor-core kernel");
+        return UMNN_ERR_UNSUPPORTED;
+    }
+    p.x0 = x0; p.x = x; p.h = h; p.nodes = nodes; p.weights = weights; p.blobs = (const uint8_t*)packed;
+    p.out = nullptr; p.out_fx = nullptr; p.out_fx0 = nullptr;
+    p.slot0 = slot0; p.n_slots = n_slots_chunk; p.slots_per_cta = slots_per_cta; p.tiles_per_cta = tiles_per_cta;
+    p.D = d->n_dims; p.E = d->n_ctx; p.layout = d->layout; p.Q = d->nb_steps; p.out_act = d->out_act;
+    p.rps = d->nb_steps + 3;
+    p.x_row = 1;
+    p.S = make_tc_smem(p.L, p.rps, p.Q);
+    p.emit = emit;
+    if (p.S.total > kTcMaxSmem) {
+        set_error("BF16X3 backward: needs %u bytes of shared memory (max %zu)", p.S.total, kTcMaxSmem);
+        return UMNN_ERR_UNSUPPORTED;
+    }
+    auto kern = d->hidden_act == UMNN_ACT_LEAKY_RELU ? cc_forward_tc_kernel<UMNN_ACT_LEAKY_RELU, true>
+                                                     : cc_forward_tc_kernel<UMNN_ACT_RELU, true>;
+    UMNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.S.total));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)n_cta);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = p.S.total;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    UMNN_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
+    return 0;
+}
+
+bool tc_two_segments_public() { return tc_two_segments(); }
 
 }  // namespace umnn

@@ -1,0 +1,197 @@
+// Layouts of the tensor-core backward (three passes over a chunk of rows, see cc_backward_tc.cu):
+//   pass F  forward re-evaluation (cc_forward_tc_kernel<.., EMIT>) -> activation panels A_0..A_J, sign masks, v
+//   pass D  dgrad chain with transposed weights -> dz panels DZ_1..DZ_{J+1}, d_h, d_x, d_x0
+//   pass W  split-K weight-gradient GEMMs over the panels (tcgen05 SS, MN-major operands)
+//
+// Hidden layers j = 1..J (J = n_layers - 1), widths H_j padded to P_j = tc_pad(H_j) exactly as in the
+// forward (units H_j and H_j + 1 carry the constant 1.0, so column H_j of A_j is the "ones" column that
+// turns the bias gradient into one more column of the weight-gradient GEMM).  A_0 = [x_row, h_slot, 1, 0..]
+// has width P_0 = round_up(1 + E + 1, 16).
+//
+// A panel of width W stores bf16 values for R_pad rows in blocks of 16 rows, each block being a ready-made
+// MN-major UMMA operand tile: [k8 = (row % 16) / 8][col / 8][row % 8][col % 8]  (128-byte core matrices, one
+// 16-byte granule = 8 consecutive columns of one row).  The pass-W producer therefore moves contiguous
+// blocks with bulk-TMA copies and the MMA descriptors are LBO = (tile_cols/8)*128, SBO = 128.
+#pragma once
+
+#include "tc_layout.cuh"
+
+namespace umnn {
+
+constexpr int kBwdMaxHidden = UMNN_MAX_LAYERS - 1;          // J <= 7
+constexpr int kBwdMaxTiles = 8;                             // tiles of 128 rows per CTA and chunk
+
+__host__ __device__ inline size_t panel_offset(long long pr, int c, int W) {
+    return (size_t)(pr >> 4) * (size_t)(32 * W) + (size_t)(((pr >> 3) & 1) * (W >> 3) + (c >> 3)) * 128 +
+           (size_t)(pr & 7) * 16 + (size_t)(c & 7) * 2;
+}
+
+struct TcChainLayer {
+    int kpad, npad;
+    int nseg, seg_begin[2], seg_n[2];
+    uint32_t b_off[2][2];
+};
+
+// dgrad chain: layer i maps dz_{J-i} (width kpad = P_{J-i}) to da_{J-i-1} (width npad = P_{J-i-1}, or the
+// padded input width for the last one) with B'_i[n'][k'] = W_{J-i}[k'][n'] (no bias carriers)
+struct TcDgradLayout {
+    int J;
+    int H[kBwdMaxHidden + 2];   // H[0] = 1 + E (inputs), H[1..J] hidden widths
+    int P[kBwdMaxHidden + 2];   // padded panel widths P[0..J]
+    int n0pad;                  // padded width of the last dgrad output (inputs), multiple of 32
+    TcChainLayer layer[kBwdMaxHidden];
+    uint32_t off_wlast;         // fp32 w_{J+1}[P_J] (zero beyond H_J: no bias)
+    uint32_t weights_bytes, blob_bytes;
+    int src_w_off[UMNN_MAX_LAYERS], src_b_off[UMNN_MAX_LAYERS];
+};
+
+inline void tc_cut_segments(TcChainLayer* y, bool two_segments) {
+    const int pairs = (y->npad + 31) / 32;
+    const int n0 = 32 * ((pairs + 1) / 2);
+    if (two_segments && y->npad - n0 >= 32) {
+        y->nseg = 2;
+        y->seg_begin[0] = 0;  y->seg_n[0] = n0;
+        y->seg_begin[1] = n0; y->seg_n[1] = y->npad - n0;
+    } else {
+        y->nseg = 1;
+        y->seg_begin[0] = 0;  y->seg_n[0] = y->npad;
+        y->seg_begin[1] = y->npad; y->seg_n[1] = 0;
+    }
+}
+
+inline bool make_tc_dgrad_layout(const umnn_desc* d, TcDgradLayout* L, bool two_segments = true) {
+    if (d->n_layers < 3) return false;
+    *L = TcDgradLayout{};
+    L->J = d->n_layers - 1;
+    int src = 0;
+    for (int l = 0; l < d->n_layers; ++l) {
+        L->src_w_off[l] = src;
+        src += d->widths[l] * d->widths[l + 1];
+        L->src_b_off[l] = src;
+        src += d->widths[l + 1];
+    }
+    L->H[0] = d->widths[0];
+    L->P[0] = round_up(d->widths[0] + 1, 16);
+    for (int j = 1; j <= L->J; ++j) {
+        L->H[j] = d->widths[j];
+        L->P[j] = tc_pad(d->widths[j]);
+        if (L->P[j] > kTcRegionCols) return false;
+    }
+    L->n0pad = round_up(d->widths[0], 32);
+    if (L->n0pad > 64 || L->P[0] > 64) return false;   // the input-gradient tile is reduced through shared memory
+    uint32_t off = 0;
+    for (int i = 0; i < L->J; ++i) {
+        TcChainLayer& y = L->layer[i];
+        y.kpad = L->P[L->J - i];
+        y.npad = (i < L->J - 1) ? L->P[L->J - i - 1] : L->n0pad;
+        tc_cut_segments(&y, two_segments);
+        for (int part = 0; part < 2; ++part)
+            for (int s = 0; s < y.nseg; ++s) {
+                y.b_off[part][s] = off;
+                off += (uint32_t)(y.seg_n[s] / 2) * y.kpad * 2;
+            }
+    }
+    L->weights_bytes = off;
+    L->off_wlast = off;
+    off += 4u * L->P[L->J];
+    L->blob_bytes = (off + 15u) & ~15u;
+    return true;
+}
+
+// shared-memory map of the dgrad kernel
+struct TcDgradSmem {
+    uint32_t off_dv, off_f, off_node, off_d0, off_carry, off_tabw, off_bars, off_holder, total;
+};
+constexpr int kTcDgradBars = kBwdMaxHidden * 10 + 2 * kTcPrepBufs + 2;
+
+inline TcDgradSmem make_tc_dgrad_smem(const TcDgradLayout& L, int E, int Q) {
+    TcDgradSmem S{};
+    uint32_t off = L.blob_bytes;
+    S.off_dv = off;    off += 4u * kTcPrepBufs * kTcTile;
+    S.off_f = off;     off += 4u * kTcPrepBufs * kTcTile;
+    S.off_node = off;  off += 4u * kTcPrepBufs * kTcTile;
+    S.off_d0 = off;    off += 4u * kTcTile * (L.n0pad + 1);
+    S.off_carry = off; off += 4u * 2 * (E > 0 ? E : 1);
+    S.off_tabw = off;  off += 4u * (Q + 1);
+    off = (off + 7u) & ~7u;
+    S.off_bars = off;  off += 8u * kTcDgradBars;
+    S.off_holder = off; off += 16;
+    S.total = off + 1024;
+    return S;
+}
+
+// ---- pass W: one accumulator per Linear layer, all resident in TMEM at once -------------------------
+struct TcWgradLayer {
+    int m_width, n_width;       // panel widths of the M operand (256 rows of D over the CTA pair) and N operand
+    int m_panel, n_panel;       // indices into the panel table
+    int tmem_col;               // first accumulator column
+    int n_half;                 // N columns staged per CTA (n_width / 2)
+    int swapped;                // 1: D rows = input units (last Linear layer), 0: D rows = output units
+    int lin;                    // Linear layer index in the flat vector
+    int n_out, n_in, ones_col;  // true dims; column (or row when swapped) that carries the bias gradient
+};
+
+struct TcWgradPlan {
+    int n_layers;               // = J + 1
+    TcWgradLayer layer[UMNN_MAX_LAYERS];
+    int n_panels;               // panel table: A_0..A_J then DZ_1..DZ_{J+1}; each has hi and lo
+    int panel_width[2 * UMNN_MAX_LAYERS + 2];
+    uint32_t stage_bytes;       // bytes staged per 16-row K block and CTA
+    uint32_t tile_off[2 * UMNN_MAX_LAYERS + 2][2];   // smem offset of panel tile [panel][hi/lo] inside a stage
+    int tile_cols[2 * UMNN_MAX_LAYERS + 2];          // columns staged per CTA for that panel (half or 128)
+    int tile_is_m[2 * UMNN_MAX_LAYERS + 2];
+    int tmem_cols_used;
+};
+
+// panel indices
+inline int panel_A(int j) { return j; }                             // j = 0..J
+inline int panel_DZ(int j, int J) { return J + j; }                 // j = 1..J+1  -> J+1 .. 2J+1
+
+inline bool make_tc_wgrad_plan(const TcDgradLayout& G, TcWgradPlan* W) {
+    *W = TcWgradPlan{};
+    const int J = G.J;
+    W->n_layers = J + 1;
+    W->n_panels = 2 * J + 2;
+    for (int j = 0; j <= J; ++j) W->panel_width[panel_A(j)] = G.P[j];
+    for (int j = 1; j <= J; ++j) W->panel_width[panel_DZ(j, J)] = G.P[j];
+    W->panel_width[panel_DZ(J + 1, J)] = 16;
+    int col = 0;
+    for (int j = 1; j <= J + 1; ++j) {
+        TcWgradLayer& y = W->layer[j - 1];
+        y.lin = j - 1;
+        y.n_in = G.H[j - 1];
+        y.n_out = (j <= J) ? G.H[j] : 1;
+        y.swapped = (j == J + 1);
+        if (!y.swapped) {
+            y.m_panel = panel_DZ(j, J);  y.m_width = G.P[j];
+            y.n_panel = panel_A(j - 1);  y.n_width = G.P[j - 1];
+            y.ones_col = G.H[j - 1];            // column of A_{j-1} that holds 1.0 (for A_0: index 1+E)
+        } else {
+            y.m_panel = panel_A(J);      y.m_width = G.P[J];
+            y.n_panel = panel_DZ(J + 1, J); y.n_width = 16;
+            y.ones_col = G.H[J];                // ROW of D (unit H_J of A_J holds 1.0)
+        }
+        if (y.m_width > 256 || (y.n_width % 16) != 0) return false;
+        y.n_half = y.n_width / 2;
+        y.tmem_col = col;
+        col += y.n_width;
+    }
+    W->tmem_cols_used = col;
+    if (col > 512) return false;
+    // per-stage tiles: every panel is the M operand of exactly one layer or the N operand of exactly one
+    for (int p = 0; p < W->n_panels; ++p) { W->tile_cols[p] = 0; W->tile_is_m[p] = 0; }
+    for (int l = 0; l < W->n_layers; ++l) {
+        W->tile_cols[W->layer[l].m_panel] = 128;  W->tile_is_m[W->layer[l].m_panel] = 1;
+        W->tile_cols[W->layer[l].n_panel] = W->layer[l].n_half;
+    }
+    uint32_t off = 0;
+    for (int p = 0; p < W->n_panels; ++p)
+        for (int part = 0; part < 2; ++part) {
+            W->tile_off[p][part] = off;
+            off += (uint32_t)W->tile_cols[p] * 16 * 2;
+        }
+    W->stage_bytes = off;
+    return true;
+}
+
+}  // namespace umnn

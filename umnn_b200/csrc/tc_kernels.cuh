@@ -1,0 +1,55 @@
+// Parameter blocks shared by the tensor-core kernels (forward / pass F, pass D, pass W).
+#pragma once
+
+#include "tc_bwd_layout.cuh"
+#include "tc_layout.cuh"
+
+namespace umnn {
+
+// panels written by pass F (EMIT) for one chunk of rows; index j = hidden layer (0 = network input)
+struct TcEmit {
+    uint8_t* a_hi[UMNN_MAX_LAYERS];
+    uint8_t* a_lo[UMNN_MAX_LAYERS];
+    uint32_t* mask[UMNN_MAX_LAYERS];   // [R_pad][8] sign bits per 32-column pair, j = 1..J
+    float* v;                          // [R_pad] pre-output-activation
+    int width[UMNN_MAX_LAYERS];        // panel widths P_j
+    long long row_block;               // padded rows per CTA (tiles_per_cta * 128)
+};
+
+struct TcParams {
+    const float* x0;
+    const float* x;
+    const float* h;
+    const float* nodes;
+    const float* weights;
+    const uint8_t* blobs;  // [2][blob_bytes]
+    float* out;
+    float* out_fx;
+    float* out_fx0;
+    long long slot0;       // first slot served by this launch (chunked launches of the backward)
+    long long n_slots;     // slots served by this launch
+    long long slots_per_cta;
+    int tiles_per_cta;
+    int D, E, layout, Q, rps, out_act;
+    int x_row;             // 1: the first extra row of a slot (node Q+1) is evaluated at x, else at x0
+    TcLayout L;
+    TcSmem S;
+    TcEmit emit;
+};
+
+int launch_forward_tc_emit(const umnn_desc* d, const float* x0, const float* x, const float* h, const void* packed,
+                           const float* nodes, const float* weights, long long slot0, long long n_slots_chunk,
+                           long long slots_per_cta, int tiles_per_cta, int n_cta, const TcEmit& emit, cudaStream_t s);
+bool tc_two_segments_public();
+
+// tensor-core backward (cc_backward_tc.cu)
+const char* backward_tc_unsupported_reason(const umnn_desc* d);
+size_t backward_tc_workspace_bytes(const umnn_desc* d);
+size_t backward_tc_packed_bytes(const umnn_desc* d);      // forward blobs + dgrad blobs
+int launch_pack_backward_tc(const umnn_desc* d, const float* flat, void* packed, cudaStream_t s);
+int launch_backward_tc(const umnn_desc* d, const float* x0, const float* x, const float* h, const void* packed,
+                       const float* nodes, const float* weights, const float* grad_out, const float* grad_fx,
+                       float* d_x0, float* d_x, float* d_h, float* d_params, void* workspace, size_t workspace_bytes,
+                       cudaStream_t s);
+
+}  // namespace umnn

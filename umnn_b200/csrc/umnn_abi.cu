@@ -8,6 +8,7 @@
 
 #include "umnn_common.cuh"
 #include "tc_layout.cuh"
+#include "tc_kernels.cuh"
 
 namespace umnn {
 
@@ -136,7 +137,10 @@ size_t umnn_packed_params_bytes(const umnn_desc* d) {
     if (validate_desc(d) != 0) return 0;
     switch (resolve_precision(d)) {
         case UMNN_PREC_FP32: return sizeof(float) * (size_t)make_fp32_layout(d).total_floats;
-        case UMNN_PREC_BF16X3: return check_tc(d, "umnn_packed_params_bytes") ? 0 : tc_packed_bytes(d);
+        case UMNN_PREC_BF16X3:
+            if (check_tc(d, "umnn_packed_params_bytes")) return 0;
+            // forward blobs, followed by the transposed (dgrad) blobs when the tensor-core backward serves the shape
+            return backward_tc_unsupported_reason(d) ? tc_packed_bytes(d) : backward_tc_packed_bytes(d);
         default: return 0;
     }
 }
@@ -150,7 +154,8 @@ int umnn_pack_params(const umnn_desc* d, const float* flat_params, void* params_
             return launch_pack_fp32(d, flat_params, (float*)params_packed, (cudaStream_t)stream);
         case UMNN_PREC_BF16X3:
             if ((rc = check_tc(d, "umnn_pack_params")) != 0) return rc;
-            return launch_pack_tc(d, flat_params, params_packed, (cudaStream_t)stream);
+            if (backward_tc_unsupported_reason(d)) return launch_pack_tc(d, flat_params, params_packed, (cudaStream_t)stream);
+            return launch_pack_backward_tc(d, flat_params, params_packed, (cudaStream_t)stream);
         default:
             set_error("umnn_pack_params: precision %d is not available for this shape", d->precision);
             return UMNN_ERR_UNSUPPORTED;
@@ -160,6 +165,14 @@ int umnn_pack_params(const umnn_desc* d, const float* flat_params, void* params_
 size_t umnn_workspace_bytes(const umnn_desc* d, int32_t for_backward) {
     if (validate_desc(d) != 0) return 0;
     if (!for_backward) return 0;
+    if (resolve_precision(d) == UMNN_PREC_BF16X3) {
+        const char* why = check_tc(d, "umnn_workspace_bytes") ? "forward shape unsupported" : backward_tc_unsupported_reason(d);
+        if (why) {
+            set_error("umnn_workspace_bytes: tensor-core backward unavailable for this shape (%s)", why);
+            return 0;
+        }
+        return backward_tc_workspace_bytes(d);
+    }
     if (backward_fp32_unsupported_reason(d)) {
         set_error("umnn_workspace_bytes: backward unavailable for this shape (%s)", backward_fp32_unsupported_reason(d));
         return 0;
@@ -197,10 +210,14 @@ int umnn_cc_backward(const umnn_desc* d, const float* x0, const float* x, const 
                      void* stream) {
     int rc = validate_desc(d);
     if (rc) return rc;
-    if (d->precision != UMNN_PREC_FP32) {
-        set_error("umnn_cc_backward: this build runs the backward in FP32; pass desc.precision = UMNN_PREC_FP32 and "
-                  "parameters packed with that precision");
-        return UMNN_ERR_UNSUPPORTED;
+    const int prec = resolve_precision(d);
+    if (prec == UMNN_PREC_BF16X3) {
+        if ((rc = check_tc(d, "umnn_cc_backward")) != 0) return rc;
+        if (backward_tc_unsupported_reason(d)) {
+            set_error("umnn_cc_backward: tensor-core backward unavailable for this shape (%s); use UMNN_PREC_FP32",
+                      backward_tc_unsupported_reason(d));
+            return UMNN_ERR_UNSUPPORTED;
+        }
     }
     if (d->n_samples == 0) {
         if (d_params) UMNN_CUDA_TRY(cudaMemsetAsync(d_params, 0, sizeof(float) * (size_t)umnn_param_count(d), (cudaStream_t)stream));
@@ -209,6 +226,9 @@ int umnn_cc_backward(const umnn_desc* d, const float* x0, const float* x, const 
     if (!x || !params_packed || !nodes || !weights || !grad_out || (d->n_ctx > 0 && !h)) {
         set_error("umnn_cc_backward: required pointer is NULL"); return UMNN_ERR_NULL;
     }
+    if (prec == UMNN_PREC_BF16X3)
+        return launch_backward_tc(d, x0, x, h, params_packed, nodes, weights, grad_out, grad_f_at_x, d_x0, d_x, d_h, d_params,
+                                  workspace, workspace_bytes, (cudaStream_t)stream);
     return launch_backward_fp32(d, x0, x, h, (const float*)params_packed, nodes, weights, grad_out, grad_f_at_x, d_x0, d_x,
                                 d_h, d_params, workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -215,8 +215,8 @@ def _forward_common(ctx, x0, x, integrand, h, nb_steps, inv_f, parallel):
             need = ctx.needs_input_grad
             # the fused backward re-evaluates f(x), f(x0) itself; only when it cannot serve the shape are
             # the Leibniz terms taken from extra rows of the forward launch
-            ctx.native_bwd = (any(need) and os.environ.get("UMNN_B200_BACKWARD", "native") != "torch"
-                              and kernel.backward_supported(spec, x, nb_steps))
+            ctx.bwd_precision = kernel.backward_precision(spec, x, nb_steps) if any(need) else None
+            ctx.native_bwd = ctx.bwd_precision is not None
             want_fx = bool(need[1]) and not ctx.native_bwd
             want_fx0 = bool(need[0]) and not ctx.native_bwd
             out, fx, fx0 = kernel.cc_forward(spec, x0, x, h, nb_steps, want_fx=want_fx, want_fx0=want_fx0)
@@ -240,7 +240,7 @@ def _backward_common(ctx, grad_output, parallel):
     if spec is not None and ctx.native_bwd:
         d_x0, d_x, d_flat, d_h = kernel.cc_backward(spec, x0, x, h, grad_output, nb_steps, need_x0=bool(need[0]),
                                                     need_x=bool(need[1]), need_h=bool(need[4]),
-                                                    need_params=bool(need[3]))
+                                                    need_params=bool(need[3]), precision=ctx.bwd_precision)
         return d_x0, d_x, d_flat, d_h
     if spec is not None:
         grad_output = grad_output.contiguous()

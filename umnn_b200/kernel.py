@@ -137,16 +137,38 @@ def cc_forward_host(spec_widths, layout, hidden_act, out_act, flat_params, x0, x
     return out, fx, fx0
 
 
-def backward_supported(spec: KernelSpec, x: torch.Tensor, nb_steps: int) -> bool:
-    """True if umnn_cc_backward (fused FP32 backward) can serve this shape."""
+def backward_precision(spec: KernelSpec, x: torch.Tensor, nb_steps: int) -> Optional[int]:
+    """Which native backward serves this shape: PREC_BF16X3 (three tensor-core passes), PREC_FP32 (fused FFMA
+    kernel) or None (neither fits: the caller uses torch ops on the device).
+
+    UMNN_B200_BACKWARD = auto (default: tensor cores, else FFMA) | bf16x3 | fp32 | torch.
+    """
+    mode = os.environ.get("UMNN_B200_BACKWARD", "auto").lower()
+    if mode == "torch":
+        return None
+    if mode == "bf16x3":
+        cands = [_native.PREC_BF16X3]
+    elif mode == "fp32" or default_precision() == _native.PREC_FP32:
+        cands = [_native.PREC_FP32]
+    else:
+        cands = [_native.PREC_BF16X3, _native.PREC_FP32]
+    if x.shape[0] == 0:
+        return cands[-1]
     L = _native.lib()
-    desc = make_desc(spec, x, nb_steps, _native.PREC_FP32)
-    return L.umnn_workspace_bytes(desc, 1) > 0 or x.shape[0] == 0
+    for prec in cands:
+        if L.umnn_workspace_bytes(make_desc(spec, x, nb_steps, prec), 1) > 0:
+            return prec
+    return None
+
+
+def backward_supported(spec: KernelSpec, x: torch.Tensor, nb_steps: int) -> bool:
+    return backward_precision(spec, x, nb_steps) is not None
 
 
 def cc_backward(spec: KernelSpec, x0: Optional[torch.Tensor], x: torch.Tensor, h: torch.Tensor,
                 grad_out: torch.Tensor, nb_steps: int, grad_fx: Optional[torch.Tensor] = None,
-                need_x0: bool = True, need_x: bool = True, need_h: bool = True, need_params: bool = True):
+                need_x0: bool = True, need_x: bool = True, need_h: bool = True, need_params: bool = True,
+                precision: Optional[int] = None):
     """Fused backward through the C ABI: (d_x0, d_x, d_flat_params, d_h); entries not requested are None.
 
     Replaces ParallelNeuralIntegral.backward / integrate(compute_grad=True) / computeIntegrand of the
@@ -158,7 +180,11 @@ def cc_backward(spec: KernelSpec, x0: Optional[torch.Tensor], x: torch.Tensor, h
     grad_out = _as_f32c(grad_out)
     x0 = None if x0 is None else _as_f32c(x0)
     grad_fx = None if grad_fx is None else _as_f32c(grad_fx)
-    desc = make_desc(spec, x, nb_steps, _native.PREC_FP32)
+    if precision is None:
+        precision = backward_precision(spec, x, nb_steps)
+        if precision is None:
+            raise _native.NativeError(_native_err_unsupported, "no native backward serves this shape")
+    desc = make_desc(spec, x, nb_steps, precision)
     dev = x.device
     d_x0 = torch.empty_like(x) if need_x0 else None
     d_x = torch.empty_like(x) if need_x else None
