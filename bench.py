@@ -200,6 +200,40 @@ def torch_route_probe(net, cfg, dev, Bs=256, reps=3):
             "what": "reference algorithm as PyTorch-CUDA ops (fp32, TF32 off), sub-batch, same B200"}
 
 
+def backward_probe(net, cfg, dev, reps=3):
+    """Informational: the Leibniz backward (d_x0, d_x, d_h, d_params) on a sub-batch through the three paths."""
+    import torch
+    from umnn_b200 import _native, kernel
+    from umnn_b200.integral import _integrate_grads_chunked
+    D, E, Q = cfg["D"], cfg["E"], cfg["Q"]
+    Hh = E * D if cfg["layout"] == "strided" else E
+    Bs = max(1, min(cfg["B"], 2_000_000 // (D * (Q + 3))))
+    g = torch.Generator(device=dev).manual_seed(11)
+    x = 2 * torch.randn(Bs, D, device=dev, generator=g)
+    h = torch.randn(Bs, Hh, device=dev, generator=g)
+    go = torch.randn(Bs, D, device=dev, generator=g)
+    x0 = torch.zeros_like(x)
+    ks = net.kernel_spec()
+    res = {"sample_batch": Bs, "rows": Bs * D * (Q + 3)}
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / reps
+
+    for label, prec in (("bf16x3_tensor_core_ms", _native.PREC_BF16X3), ("fp32_ffma_ms", _native.PREC_FP32)):
+        if _native.lib().umnn_workspace_bytes(kernel.make_desc(ks, x, Q, prec), 1) > 0:
+            res[label] = timed(lambda: kernel.cc_backward(ks, x0, x, h, go, Q, precision=prec))
+    res["torch_ops_reference_algorithm_ms"] = timed(lambda: _integrate_grads_chunked(x0, x, net, h, Q, go, False))
+    return res
+
+
 def run_ours(args, cfg, name):
     import torch
     import torch.distributed as dist
@@ -354,7 +388,8 @@ def run_ours(args, cfg, name):
     }
     if world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_arm(cfg, spec, flat)[0]
-        out["aux"] = {"torch_cuda_reference_algorithm": torch_route_probe(net, cfg, dev)}
+        out["aux"] = {"torch_cuda_reference_algorithm": torch_route_probe(net, cfg, dev),
+                      "backward": backward_probe(net, cfg, dev)}
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

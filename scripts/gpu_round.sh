@@ -22,4 +22,11 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --cs
 echo "== ncu full capture of the forward kernel"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:cc_forward -s 2 -c 1 -o $OUT/prof_fwd \
     python bench.py --steps 1 --warmup 1 --batch 8192 --no-cpu > $OUT/prof_bench.log 2>&1
+echo "== ncu captures of the backward passes"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:cc_dgrad_tc -s 1 -c 1 -o $OUT/prof_dgrad \
+    python scripts/bwd_tc_bringup.py cfg3 > $OUT/prof_dgrad.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:cc_wgrad_tc -s 1 -c 1 -o $OUT/prof_wgrad \
+    python scripts/bwd_tc_bringup.py cfg3 > $OUT/prof_wgrad.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 60 --csv --log-file $OUT/launches_bwd.csv \
+    python scripts/bwd_tc_bringup.py cfg3 > $OUT/launches_bwd.log 2>&1
 ls -la $OUT
