@@ -505,39 +505,44 @@ __global__ void __launch_bounds__(kWThreads, 1) cc_wgrad_tc_kernel(const __grid_
     const uint32_t tbase = holder;
 
     if (warp == kWEpiWarps) {
-        // =========================================================== producer: bulk-TMA the panel tiles of a block
+        // =========================================================== producer: bulk-TMA the panel tiles of a block.
+        // The <= 64 copies of one block (panel x hi/lo x k8 half) are spread over the lanes of the warp.
+        __shared__ uint32_t cp_dst[64], cp_bytes[64];
+        __shared__ unsigned long long cp_src[64], cp_blk_stride[64];
+        __shared__ uint32_t n_copies_s, total_bytes_s;
         if (lane == 0) {
-            // bytes this CTA stages per block
-            uint32_t bytes = 0;
+            uint32_t n = 0, bytes = 0;
             for (int pn = 0; pn < W.n_panels; ++pn) {
                 const int Wd = W.panel_width[pn];
                 int c0, nc;
                 if (W.tile_is_m[pn]) { c0 = 128 * (int)rank; nc = Wd - c0; if (nc > 128) nc = 128; if (nc < 0) nc = 0; }
                 else { nc = W.tile_cols[pn]; c0 = nc * (int)rank; }
-                bytes += 2u * 2u * (uint32_t)(nc / 8) * 128u;
-            }
-            for (long long kb = 0; kb < n_kb; ++kb) {
-                const int st = (int)(kb % kWStages);
-                if (kb >= kWStages) mbar_wait(&empty[st], (uint32_t)((kb / kWStages - 1) & 1), 400 + st);
-                mbar_expect_tx(&full[st], bytes);
-                uint8_t* sb = smem + (size_t)st * W.stage_bytes;
-                const long long blk = blk_begin + kb;
-                for (int pn = 0; pn < W.n_panels; ++pn) {
-                    const int Wd = W.panel_width[pn];
-                    int c0, nc;
-                    if (W.tile_is_m[pn]) { c0 = 128 * (int)rank; nc = Wd - c0; if (nc > 128) nc = 128; if (nc < 0) nc = 0; }
-                    else { nc = W.tile_cols[pn]; c0 = nc * (int)rank; }
-                    if (nc == 0) continue;
-                    const int tile_cols = W.tile_cols[pn];
-                    for (int part = 0; part < 2; ++part) {
-                        const uint8_t* src = p.panel[pn][part] + (size_t)blk * (size_t)(32 * Wd);
-                        uint8_t* dst = sb + W.tile_off[pn][part];
-                        for (int k8 = 0; k8 < 2; ++k8)
-                            bulk_g2s(dst + (size_t)k8 * (tile_cols / 8) * 128, src + (size_t)(k8 * (Wd / 8) + c0 / 8) * 128,
-                                     (uint32_t)(nc / 8) * 128u, &full[st]);
+                if (nc == 0) continue;
+                const int tile_cols = W.tile_cols[pn];
+                for (int part = 0; part < 2; ++part)
+                    for (int k8 = 0; k8 < 2; ++k8) {
+                        cp_dst[n] = W.tile_off[pn][part] + (uint32_t)k8 * (tile_cols / 8) * 128u;
+                        cp_src[n] = (unsigned long long)(p.panel[pn][part] + (size_t)(k8 * (Wd / 8) + c0 / 8) * 128);
+                        cp_blk_stride[n] = (unsigned long long)(32 * Wd);
+                        cp_bytes[n] = (uint32_t)(nc / 8) * 128u;
+                        bytes += cp_bytes[n];
+                        ++n;
                     }
-                }
             }
+            n_copies_s = n;
+            total_bytes_s = bytes;
+        }
+        __syncwarp();
+        const uint32_t n_copies = n_copies_s, bytes = total_bytes_s;
+        for (long long kb = 0; kb < n_kb; ++kb) {
+            const int st = (int)(kb % kWStages);
+            if (kb >= kWStages) mbar_wait(&empty[st], (uint32_t)((kb / kWStages - 1) & 1), 400 + st);
+            if (lane == 0) mbar_expect_tx(&full[st], bytes);
+            __syncwarp();
+            uint8_t* sb = smem + (size_t)st * W.stage_bytes;
+            const unsigned long long blk = (unsigned long long)(blk_begin + kb);
+            for (uint32_t i = lane; i < n_copies; i += 32)
+                bulk_g2s(sb + cp_dst[i], reinterpret_cast<const uint8_t*>(cp_src[i] + blk * cp_blk_stride[i]), cp_bytes[i], &full[st]);
         }
         __syncwarp();
     } else if (warp == kWEpiWarps + 1) {
