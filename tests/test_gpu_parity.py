@@ -493,3 +493,26 @@ def test_training_curves_agree_between_backward_paths(monkeypatch):
     tc = train("bf16x3")
     assert ref[-1] < ref[0] - 0.1                                  # it actually trains
     assert np.max(np.abs(tc - ref)) < 2e-3 * max(1.0, np.max(np.abs(ref)))
+
+
+def test_fused_flow_block_matches_unfused():
+    """UMNNMAF.forward_and_log_jac on the kernel route (integral + Jacobian point from one launch, Jacobian
+    cotangent folded into the fused backward) against forward() + the torch evaluation of the Jacobian."""
+    from umnn_b200 import EmbeddingNetwork, UMNNMAF
+    torch.manual_seed(0)
+    emb = EmbeddingNetwork(6, [64, 64], [200, 200, 200], 30, device=_dev())
+    blk = UMNNMAF(emb, 6, 50, _dev(), solver="CCParallel").to(_dev())
+    x = torch.randn(128, 6, device=_dev())
+    outs = []
+    for fused in (True, False):
+        for p in blk.parameters():
+            p.grad = None
+        xx = x.clone().requires_grad_(True)
+        z, lj = blk.forward_and_log_jac(xx) if fused else blk.compute_log_jac_bis(xx)
+        (z.pow(2).sum() + lj.sum()).backward()
+        outs.append((z.detach(), lj.detach(), xx.grad.clone(),
+                     torch.cat([p.grad.reshape(-1) for p in blk.parameters() if p.grad is not None])))
+    (z1, l1, gx1, gp1), (z2, l2, gx2, gp2) = outs
+    assert torch.allclose(z1, z2, rtol=1e-5, atol=1e-5) and torch.allclose(l1, l2, rtol=1e-5, atol=1e-5)
+    assert _norm_err(gx1.cpu().numpy(), gx2.cpu().numpy()) < 5e-3
+    assert _norm_err(gp1.cpu().numpy(), gp2.cpu().numpy()) < 5e-3

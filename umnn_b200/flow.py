@@ -17,7 +17,8 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .integral import NeuralIntegral, ParallelNeuralIntegral, integral_nograd
+from .integral import (FusedIntegralAndPoint, NeuralIntegral, ParallelNeuralIntegral, fused_point_available,
+                       integral_nograd)
 from .networks import (ConditionnalMADE, ContiguousIntegrand, IntegrandNN, IntegrandNetwork, MADE, _flatten, _mlp)
 from .quadrature import compute_cc_weights
 
@@ -117,7 +118,19 @@ class UMNNMAF(nn.Module):
         return z, self._log_jac_from_embedding(x)
 
     def forward_and_log_jac(self, x, context=None):
-        """(z, log|dz/dx|) with ONE conditioner pass (the reference recomputes MADE, UMNNMAF.py:79,137)."""
+        """(z, log|dz/dx|) with ONE conditioner pass (the reference recomputes MADE, UMNNMAF.py:79,137) and, on
+        the kernel route, ONE fused launch for the integral and the Jacobian point f(x, h)."""
+        if self.solver in ("CC", "CCParallel") and x.is_cuda and not (torch.jit.is_tracing() or torch.jit.is_scripting()):
+            x0 = torch.zeros_like(x)
+            h = self.net.make_embeding(x, context)
+            nets = self.net.parallel_nets
+            needs_grad = torch.is_grad_enabled() and (x.requires_grad or h.requires_grad or
+                                                      any(p.requires_grad for p in nets.parameters()))
+            if fused_point_available(nets, x0, x, h, self.nb_steps, needs_grad):
+                z0 = h.view(h.shape[0], -1, x.shape[1])[:, 0, :]
+                integral, jac = FusedIntegralAndPoint.apply(x0, x, nets, _flatten(nets.parameters()), h, self.nb_steps)
+                scale = self._scale(x.shape[0])
+                return torch.exp(scale) * (integral + z0), torch.log(jac + 1e-10) + scale
         return self.compute_log_jac_bis(x, context=context)
 
     def compute_ll(self, x, context=None):

@@ -270,6 +270,48 @@ def _backward_common(ctx, grad_output, parallel):
     return d_x0, d_x, g_param, g_h.view(h.shape)
 
 
+class FusedIntegralAndPoint(torch.autograd.Function):
+    """apply(x0, x, integrand, flat_params, h, nb_steps) -> (integral, f(x, h)) from ONE fused launch.
+
+    Kernel route only.  Serves UMNNMAF.forward + compute_log_jac together (UMNNMAF.py:76-139): the Jacobian
+    point is an extra row of the forward launch, and its cotangent enters the fused backward as
+    `grad_f_at_x` instead of a second pass through the integrand network.
+    """
+
+    @staticmethod
+    def forward(ctx, x0, x, integrand, flat_params, h, nb_steps):
+        spec = kernel_route(integrand, x0, x, h, False)
+        if spec is None:
+            raise ValueError("FusedIntegralAndPoint needs the kernel route")
+        ctx.kernel_spec, ctx.nb_steps = spec, nb_steps
+        ctx.bwd_precision = kernel.backward_precision(spec, x, nb_steps) if any(ctx.needs_input_grad) else None
+        if any(ctx.needs_input_grad) and ctx.bwd_precision is None:
+            raise ValueError("FusedIntegralAndPoint: no native backward serves this shape")
+        with torch.no_grad():
+            out, fx, _ = kernel.cc_forward(spec, x0, x, h, nb_steps, want_fx=True)
+            ctx.save_for_backward(x0.clone(), x.clone(), h)
+        return out, fx
+
+    @staticmethod
+    def backward(ctx, grad_out, grad_fx):
+        x0, x, h = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        if grad_out is None:
+            grad_out = torch.zeros_like(x)
+        d_x0, d_x, d_flat, d_h = kernel.cc_backward(ctx.kernel_spec, x0, x, h, grad_out, ctx.nb_steps, grad_fx=grad_fx,
+                                                    need_x0=bool(need[0]), need_x=bool(need[1]), need_h=bool(need[4]),
+                                                    need_params=bool(need[3]), precision=ctx.bwd_precision)
+        return d_x0, d_x, None, d_flat, d_h, None
+
+
+def fused_point_available(integrand, x0, x, h, nb_steps, needs_grad):
+    """True if FusedIntegralAndPoint can serve this call (kernel route, and a native backward when needed)."""
+    spec = kernel_route(integrand, x0, x, h, False)
+    if spec is None:
+        return False
+    return (not needs_grad) or kernel.backward_precision(spec, x, nb_steps) is not None
+
+
 class ParallelNeuralIntegral(torch.autograd.Function):
     """apply(x0, x, integrand, flat_params, h, nb_steps=20, inv_f=False) -> integral [B, Dx]."""
 
