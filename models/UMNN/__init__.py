@@ -1,12 +1,16 @@
-"""Import-path shim for the reference's `models.UMNN` package (models/UMNN/__init__.py:1-6).
+"""Import-path shim for the reference's `models.UMNN` package (reference: models/UMNN/__init__.py:1-6).
 
-As in the reference, `models.UMNN.NeuralIntegral` / `models.UMNN.ParallelNeuralIntegral` resolve to the
-autograd Function classes while `from models.UMNN.ParallelNeuralIntegral import integrate` still reaches
-the submodule.
+As there, `models.UMNN.NeuralIntegral` / `models.UMNN.ParallelNeuralIntegral` name the autograd Function
+classes (the class import shadows the submodule attribute), while
+`from models.UMNN.ParallelNeuralIntegral import integrate` still reaches the submodule through sys.modules.
+Everything is served by the `umnn_b200` package.
 """
-from .UMNNMAFFlow import UMNNMAFFlow  # noqa: F401
-from .MonotonicNN import MonotonicNN, IntegrandNN  # noqa: F401
-from .UMNNMAF import IntegrandNetwork, UMNNMAF  # noqa: F401
-from .made import MADE  # noqa: F401
-from .NeuralIntegral import NeuralIntegral  # noqa: F401
-from .ParallelNeuralIntegral import ParallelNeuralIntegral  # noqa: F401
+from .made import MADE
+from .MonotonicNN import IntegrandNN, MonotonicNN
+from .UMNNMAF import UMNNMAF, IntegrandNetwork
+from .UMNNMAFFlow import UMNNMAFFlow
+from .NeuralIntegral import NeuralIntegral          # the class, not the module
+from .ParallelNeuralIntegral import ParallelNeuralIntegral
+
+__all__ = ["MADE", "IntegrandNN", "MonotonicNN", "UMNNMAF", "IntegrandNetwork", "UMNNMAFFlow", "NeuralIntegral",
+           "ParallelNeuralIntegral"]

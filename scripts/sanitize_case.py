@@ -1,0 +1,30 @@
+"""Tiny forward + backward through every kernel family (run under compute-sanitizer)."""
+import os, sys
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+import numpy as np, torch
+from oracle import umnn_oracle as orc
+from umnn_b200 import IntegrandNetwork, kernel, _native, cc_integrate
+
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+B, D, E, hidden, Q = 24, 3, 6, [40, 24, 24], 30
+spec = orc.MLPSpec(tuple([1 + E] + hidden + [1]))
+flat = orc.synth_params(spec, 0, 1.5)
+x0, x, h, g = orc.synth_inputs(B, D, E * D, 1, x0_zero=False)
+net = IntegrandNetwork(D, 1 + E, hidden, 1)
+off = 0
+with torch.no_grad():
+    for p in net.parameters():
+        p.copy_(torch.from_numpy(flat[off:off + p.numel()].copy()).view_as(p)); off += p.numel()
+dev = torch.device("cuda:0"); net.to(dev).eval()
+t = [torch.from_numpy(a).to(dev) for a in (x0, x, h, g)]
+ks = net.kernel_spec()
+ref = orc.integrate_parallel(spec, flat, x0, x, h, Q)
+for name, prec in (("fp32", _native.PREC_FP32), ("bf16x3", _native.PREC_BF16X3)):
+    if which not in ("all", name):
+        continue
+    out, fx, fx0 = cc_integrate(net, t[0], t[1], t[2], Q, want_fx=True, want_fx0=True, precision=prec)
+    grads = kernel.cc_backward(ks, t[0], t[1], t[2], t[3], Q, grad_fx=t[3], precision=prec)
+    torch.cuda.synchronize()
+    err = float(np.max(np.abs(out.cpu().numpy() - ref) / np.maximum(np.abs(ref), 1e-6)))
+    print(f"{name}: forward rel-err {err:.2e}, |d_params| {float(grads[2].abs().sum()):.4f}", flush=True)

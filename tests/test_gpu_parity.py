@@ -516,3 +516,31 @@ def test_fused_flow_block_matches_unfused():
     assert torch.allclose(z1, z2, rtol=1e-5, atol=1e-5) and torch.allclose(l1, l2, rtol=1e-5, atol=1e-5)
     assert _norm_err(gx1.cpu().numpy(), gx2.cpu().numpy()) < 5e-3
     assert _norm_err(gp1.cpu().numpy(), gp2.cpu().numpy()) < 5e-3
+
+
+def test_cuda_graph_capture_and_replay():
+    """The fused launch is stream-ordered and allocation-light: an eval-mode forward (integral + Jacobian
+    point) can be captured in a CUDA graph and replayed on new inputs (the latency path for small batches)."""
+    from umnn_b200 import cc_integrate
+    spec = orc.MLPSpec((31, 100, 50, 50, 50, 50, 1))
+    flat = orc.synth_params(spec, 0, 1.0)
+    net = _net_for(spec, flat, "strided", 8).eval()
+    d = _dev()
+    gen = torch.Generator(device=d).manual_seed(0)
+    x = torch.randn(12, 8, device=d, generator=gen)
+    h = torch.randn(12, 240, device=d, generator=gen)
+    cc_integrate(net, None, x, h, 50, want_fx=True)              # warm-up: packs parameters, loads tables
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        cc_integrate(net, None, x, h, 50, want_fx=True)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out, fx, _ = cc_integrate(net, None, x, h, 50, want_fx=True)
+    x.copy_(torch.randn(12, 8, device=d, generator=gen))
+    h.copy_(torch.randn(12, 240, device=d, generator=gen))
+    graph.replay()
+    torch.cuda.synchronize()
+    want, want_fx, _ = cc_integrate(net, None, x, h, 50, want_fx=True)
+    assert torch.equal(out, want) and torch.equal(fx, want_fx)
