@@ -1,0 +1,21 @@
+import os, sys
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+import numpy as np, torch
+from oracle import umnn_oracle as orc
+from umnn_b200 import IntegrandNetwork, kernel, _native
+B, D, E, hidden, Q = 10000, 6, 30, [200, 200, 200], 50
+spec = orc.MLPSpec(tuple([1 + E] + hidden + [1]))
+flat = orc.synth_params(spec, 0)
+x0, x, h, g = orc.synth_inputs(B, D, E * D, 1, x0_zero=False)
+net = IntegrandNetwork(D, 1 + E, hidden, 1)
+off = 0
+with torch.no_grad():
+    for p in net.parameters():
+        p.copy_(torch.from_numpy(flat[off:off + p.numel()].copy()).view_as(p)); off += p.numel()
+dev = torch.device("cuda:0"); net.to(dev).eval()
+t = [torch.from_numpy(a).to(dev) for a in (x0, x, h, g)]
+ks = net.kernel_spec()
+for _ in range(2):
+    kernel.cc_backward(ks, t[0], t[1], t[2], t[3], Q, precision=_native.PREC_BF16X3)
+torch.cuda.synchronize()
