@@ -36,9 +36,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB_PATH
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
-    if os.environ.get("UMNN_B200_TC_DEBUG"):
-        # bounded mbarrier spins: a protocol bug traps with a message instead of hanging the GPU
-        flags += ["-DUMNN_TC_SPIN_LIMIT=" + os.environ.get("UMNN_B200_TC_SPIN_LIMIT", "400000000LL")]
+    if os.environ.get("UMNN_B200_TC_SPIN_LIMIT"):
+        # override the bound on mbarrier polling (default 2^27, see tc_common.cuh); 0 = spin forever
+        flags += ["-DUMNN_TC_SPIN_LIMIT=" + os.environ["UMNN_B200_TC_SPIN_LIMIT"] + "LL"]
     cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + \
           [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH]
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -74,8 +74,10 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
         : "memory");
     return ok != 0;
 }
+// Bounded spinning: a protocol bug (or a faulted peer CTA) traps with a message after ~1e8 polls (seconds)
+// instead of hanging the GPU.  A legitimate wait lasts at most a few tiles (microseconds).  0 = spin forever.
 #ifndef UMNN_TC_SPIN_LIMIT
-#define UMNN_TC_SPIN_LIMIT 0  // 0 = spin forever; the probe builds with a limit so a protocol bug traps
+#define UMNN_TC_SPIN_LIMIT (1LL << 27)
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
 #if UMNN_TC_SPIN_LIMIT
