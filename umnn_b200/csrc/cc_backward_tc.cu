@@ -52,8 +52,7 @@ struct TcDgradParams {
     const uint8_t* blobs;                      // dgrad blobs [2][blob_bytes]
     const float* v;                            // [R_pad]
     const uint32_t* mask[UMNN_MAX_LAYERS];     // j = 1..J
-    uint8_t* dz_hi[UMNN_MAX_LAYERS + 1];       // j = 1..J+1
-    uint8_t* dz_lo[UMNN_MAX_LAYERS + 1];
+    uint8_t* dz[UMNN_MAX_LAYERS + 1];          // DZ_j panels, j = 1..J+1
     float *d_x0, *d_x, *d_h;
     long long slot0, n_slots, slots_per_cta, row_block;
     int tiles_per_cta, D, E, layout, Q, rps, out_act;
@@ -68,12 +67,11 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"r"(kEpiThreads) : "memory"); }
 
-__device__ __forceinline__ void emit16(uint8_t* hi, uint8_t* lo, long long pr, int col, int W, const uint32_t (&o)[16]) {
-    const size_t g0 = panel_offset(pr, col, W), g1 = panel_offset(pr, col + 8, W);
-    *reinterpret_cast<uint4*>(hi + g0) = make_uint4(o[0], o[1], o[2], o[3]);
-    *reinterpret_cast<uint4*>(hi + g1) = make_uint4(o[4], o[5], o[6], o[7]);
-    *reinterpret_cast<uint4*>(lo + g0) = make_uint4(o[8], o[9], o[10], o[11]);
-    *reinterpret_cast<uint4*>(lo + g1) = make_uint4(o[12], o[13], o[14], o[15]);
+__device__ __forceinline__ void emit16(uint8_t* panel, long long pr, int col, int W, const uint32_t (&o)[16]) {
+    *reinterpret_cast<uint4*>(panel + panel_offset(pr, col, W, 0)) = make_uint4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<uint4*>(panel + panel_offset(pr, col + 8, W, 0)) = make_uint4(o[4], o[5], o[6], o[7]);
+    *reinterpret_cast<uint4*>(panel + panel_offset(pr, col, W, 1)) = make_uint4(o[8], o[9], o[10], o[11]);
+    *reinterpret_cast<uint4*>(panel + panel_offset(pr, col + 8, W, 1)) = make_uint4(o[12], o[13], o[14], o[15]);
 }
 
 template <int HIDDEN_ACT>
@@ -220,11 +218,10 @@ __global__ void __launch_bounds__(kThreads, 1) cc_dgrad_tc_kernel(const __grid_c
                 // dz_{J+1} panel (width 16): column 0 = dv
                 uint32_t hi, lo2;
                 split_bf16x2(dv, 0.0f, hi, lo2);
-                const size_t g0 = panel_offset(pr, 0, 16), g1 = panel_offset(pr, 8, 16);
-                *reinterpret_cast<uint4*>(p.dz_hi[J + 1] + g0) = make_uint4(hi, 0u, 0u, 0u);
-                *reinterpret_cast<uint4*>(p.dz_hi[J + 1] + g1) = make_uint4(0u, 0u, 0u, 0u);
-                *reinterpret_cast<uint4*>(p.dz_lo[J + 1] + g0) = make_uint4(lo2, 0u, 0u, 0u);
-                *reinterpret_cast<uint4*>(p.dz_lo[J + 1] + g1) = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(p.dz[J + 1] + panel_offset(pr, 0, 16, 0)) = make_uint4(hi, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(p.dz[J + 1] + panel_offset(pr, 8, 16, 0)) = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(p.dz[J + 1] + panel_offset(pr, 0, 16, 1)) = make_uint4(lo2, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(p.dz[J + 1] + panel_offset(pr, 8, 16, 1)) = make_uint4(0u, 0u, 0u, 0u);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[BAR_PREP_FULL + b]);
@@ -258,7 +255,7 @@ __global__ void __launch_bounds__(kThreads, 1) cc_dgrad_tc_kernel(const __grid_c
                     split_bf16x2(z0, z1, o[i], o[8 + i]);
                 }
                 tmem_st16(tbase + lane_sel + kColQ + 32u * pp + 16u * hf, o);
-                emit16(p.dz_hi[J], p.dz_lo[J], pr, 32 * pp + 16 * hf, PJ, o);
+                emit16(p.dz[J], pr, 32 * pp + 16 * hf, PJ, o);
             }
             tmem_st_wait();
             tc_fence_before_sync();
@@ -298,14 +295,14 @@ __global__ void __launch_bounds__(kThreads, 1) cc_dgrad_tc_kernel(const __grid_c
                         split_bf16x2(__uint_as_float(v0[2 * i]) * slope_of<HIDDEN_ACT>(bits, 2 * i),
                                      __uint_as_float(v0[2 * i + 1]) * slope_of<HIDDEN_ACT>(bits, 2 * i + 1), o[i], o[8 + i]);
                     tmem_st16(taddr, o);
-                    emit16(p.dz_hi[jout], p.dz_lo[jout], pr, 32 * pp, y.npad, o);
+                    emit16(p.dz[jout], pr, 32 * pp, y.npad, o);
                     if (two) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
                             split_bf16x2(__uint_as_float(v1[2 * i]) * slope_of<HIDDEN_ACT>(bits, 16 + 2 * i),
                                          __uint_as_float(v1[2 * i + 1]) * slope_of<HIDDEN_ACT>(bits, 17 + 2 * i), o[i], o[8 + i]);
                         tmem_st16(taddr + 16, o);
-                        emit16(p.dz_hi[jout], p.dz_lo[jout], pr, 32 * pp + 16, y.npad, o);
+                        emit16(p.dz[jout], pr, 32 * pp + 16, y.npad, o);
                     }
                     tmem_st_wait();
                     tc_fence_before_sync();
@@ -452,12 +449,12 @@ __global__ void pack_dgrad_consts_kernel(const float* __restrict__ flat, uint8_t
 // ------------------------------------------------------------------------------------------------------
 // pass W
 // ------------------------------------------------------------------------------------------------------
-constexpr int kWMaxStages = 4;
+constexpr int kWMaxStages = 5;
 constexpr int kWEpiWarps = 4;
 constexpr int kWThreads = (kWEpiWarps + 2) * 32;   // warps 0-3 epilogue, 4 producer, 5 MMA
 
 struct TcWgradParams {
-    const uint8_t* panel[2 * UMNN_MAX_LAYERS + 2][2];   // [panel][hi/lo]
+    const uint8_t* panel[2 * UMNN_MAX_LAYERS + 2];      // panel base pointers
     float* part;                 // [n_pairs][P]
     long long P;                 // parameters
     long long n_blocks;          // 16-row blocks in the chunk
@@ -507,27 +504,19 @@ __global__ void __launch_bounds__(kWThreads, 1) cc_wgrad_tc_kernel(const __grid_
     if (warp == kWEpiWarps) {
         // =========================================================== producer: bulk-TMA the panel tiles of a block.
         // The <= 64 copies of one block (panel x hi/lo x k8 half) are spread over the lanes of the warp.
-        __shared__ uint32_t cp_dst[64], cp_bytes[64];
-        __shared__ unsigned long long cp_src[64], cp_blk_stride[64];
+        __shared__ uint32_t cp_dst[32], cp_bytes[32];
+        __shared__ unsigned long long cp_src[32], cp_blk_stride[32];
         __shared__ uint32_t n_copies_s, total_bytes_s;
         if (lane == 0) {
             uint32_t n = 0, bytes = 0;
             for (int pn = 0; pn < W.n_panels; ++pn) {
                 const int Wd = W.panel_width[pn];
-                int c0, nc;
-                if (W.tile_is_m[pn]) { c0 = 128 * (int)rank; nc = Wd - c0; if (nc > 128) nc = 128; if (nc < 0) nc = 0; }
-                else { nc = W.tile_cols[pn]; c0 = nc * (int)rank; }
-                if (nc == 0) continue;
-                const int tile_cols = W.tile_cols[pn];
-                for (int part = 0; part < 2; ++part)
-                    for (int k8 = 0; k8 < 2; ++k8) {
-                        cp_dst[n] = W.tile_off[pn][part] + (uint32_t)k8 * (tile_cols / 8) * 128u;
-                        cp_src[n] = (unsigned long long)(p.panel[pn][part] + (size_t)(k8 * (Wd / 8) + c0 / 8) * 128);
-                        cp_blk_stride[n] = (unsigned long long)(32 * Wd);
-                        cp_bytes[n] = (uint32_t)(nc / 8) * 128u;
-                        bytes += cp_bytes[n];
-                        ++n;
-                    }
+                cp_dst[n] = W.tile_off[pn];
+                cp_src[n] = (unsigned long long)(p.panel[pn] + (size_t)rank * (size_t)(32 * Wd));   // this CTA's column half
+                cp_blk_stride[n] = (unsigned long long)(64 * Wd);
+                cp_bytes[n] = 32u * (uint32_t)Wd;                                               // hi + lo, both K halves
+                bytes += cp_bytes[n];
+                ++n;
             }
             n_copies_s = n;
             total_bytes_s = bytes;
@@ -562,11 +551,13 @@ __global__ void __launch_bounds__(kWThreads, 1) cc_wgrad_tc_kernel(const __grid_
                 for (int l = 0; l < W.n_layers; ++l) {
                     const TcWgradLayer& y = W.layer[l];
                     const uint32_t idesc = make_idesc_bf16_f32(256, y.n_width) | (1u << 15) | (1u << 16);
-                    const uint64_t a_hi = make_smem_desc(stage_addr + W.tile_off[y.m_panel][0], 16 * 128, 128);
-                    const uint64_t a_lo = make_smem_desc(stage_addr + W.tile_off[y.m_panel][1], 16 * 128, 128);
-                    const uint32_t lbo = (uint32_t)(y.n_half / 8) * 128u;
-                    const uint64_t b_hi = make_smem_desc(stage_addr + W.tile_off[y.n_panel][0], lbo, 128);
-                    const uint64_t b_lo = make_smem_desc(stage_addr + W.tile_off[y.n_panel][1], lbo, 128);
+                    // tiles hold [hi | lo] x [k8][W/16 core matrices]; the M tile is read 128 rows deep although only
+                    // W/2 are staged (rows beyond feed accumulator rows nobody reads)
+                    const uint32_t lbo_m = (uint32_t)(y.m_width / 16) * 128u, lbo_n = (uint32_t)(y.n_width / 16) * 128u;
+                    const uint64_t a_hi = make_smem_desc(stage_addr + W.tile_off[y.m_panel], lbo_m, 128);
+                    const uint64_t a_lo = make_smem_desc(stage_addr + W.tile_off[y.m_panel] + 16u * y.m_width, lbo_m, 128);
+                    const uint64_t b_hi = make_smem_desc(stage_addr + W.tile_off[y.n_panel], lbo_n, 128);
+                    const uint64_t b_lo = make_smem_desc(stage_addr + W.tile_off[y.n_panel] + 16u * y.n_width, lbo_n, 128);
                     const uint32_t d_addr = tbase + (uint32_t)y.tmem_col;
                     if (elect_one_sync()) {
                         mma_ss<2>(d_addr, a_hi, b_hi, idesc, kb > 0);
@@ -589,10 +580,12 @@ __global__ void __launch_bounds__(kWThreads, 1) cc_wgrad_tc_kernel(const __grid_
         mbar_wait(&done, 0, 430);
         tc_fence_after_sync();
         float* out = p.part + (size_t)pair * p.P;
-        const int row = 128 * (int)rank + warp * 32 + lane;     // D row held by this thread
+        const int lane_row = warp * 32 + lane;                  // accumulator row (TMEM lane) held by this thread
         const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
         for (int l = 0; l < W.n_layers; ++l) {
             const TcWgradLayer& y = W.layer[l];
+            // CTA `rank` staged columns [rank * W/2, (rank + 1) * W/2) of the M panel as its rows 0 .. W/2 - 1
+            const int row = (lane_row < y.m_width / 2) ? (int)rank * (y.m_width / 2) + lane_row : (1 << 30);
             for (int c = 0; c < y.n_width; c += 16) {
                 uint32_t v[16];
                 tmem_ld16(tbase + lane_sel + (uint32_t)y.tmem_col + c, v);
@@ -644,7 +637,7 @@ struct BwdTcPlan {
     int rps, n_cta, tiles, n_pairs_w;
     long long slots_per_cta, chunk_slots, row_block, R_pad;
     size_t panel_bytes[2 * UMNN_MAX_LAYERS + 2];
-    size_t off_panel[2 * UMNN_MAX_LAYERS + 2][2], off_mask[UMNN_MAX_LAYERS], off_v, off_part, total_bytes;
+    size_t off_panel[2 * UMNN_MAX_LAYERS + 2], off_mask[UMNN_MAX_LAYERS], off_v, off_part, total_bytes;
     size_t w_smem;
     int w_stages;
 };
@@ -700,9 +693,8 @@ const char* make_bwd_plan(const umnn_desc* d, BwdTcPlan* B) {
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
     for (int pn = 0; pn < B->W.n_panels; ++pn) {
-        B->panel_bytes[pn] = (size_t)B->R_pad * B->W.panel_width[pn] * 2;
-        B->off_panel[pn][0] = take(B->panel_bytes[pn]);
-        B->off_panel[pn][1] = take(B->panel_bytes[pn]);
+        B->panel_bytes[pn] = (size_t)B->R_pad * B->W.panel_width[pn] * 4;      // hi + lo
+        B->off_panel[pn] = take(B->panel_bytes[pn]);
     }
     for (int j = 1; j <= B->G.J; ++j) B->off_mask[j] = take((size_t)B->R_pad * 8 * 4);
     B->off_v = take((size_t)B->R_pad * 4);
@@ -764,8 +756,7 @@ int launch_backward_tc(const umnn_desc* d, const float* x0, const float* x, cons
 
     TcEmit emit{};
     for (int j = 0; j <= J; ++j) {
-        emit.a_hi[j] = ws + B.off_panel[panel_A(j)][0];
-        emit.a_lo[j] = ws + B.off_panel[panel_A(j)][1];
+        emit.a[j] = ws + B.off_panel[panel_A(j)];
         emit.width[j] = B.G.P[j];
         if (j >= 1) emit.mask[j] = reinterpret_cast<uint32_t*>(ws + B.off_mask[j]);
     }
@@ -777,8 +768,7 @@ int launch_backward_tc(const umnn_desc* d, const float* x0, const float* x, cons
     g.blobs = dgrad_blobs; g.v = emit.v;
     for (int j = 1; j <= J; ++j) g.mask[j] = emit.mask[j];
     for (int j = 1; j <= J + 1; ++j) {
-        g.dz_hi[j] = ws + B.off_panel[panel_DZ(j, J)][0];
-        g.dz_lo[j] = ws + B.off_panel[panel_DZ(j, J)][1];
+        g.dz[j] = ws + B.off_panel[panel_DZ(j, J)];
     }
     g.d_x0 = d_x0; g.d_x = d_x; g.d_h = d_h;
     g.slots_per_cta = B.slots_per_cta; g.row_block = B.row_block; g.tiles_per_cta = B.tiles;
@@ -786,8 +776,7 @@ int launch_backward_tc(const umnn_desc* d, const float* x0, const float* x, cons
     g.L = B.G; g.S = B.GS;
 
     TcWgradParams w{};
-    for (int pn = 0; pn < B.W.n_panels; ++pn)
-        for (int part = 0; part < 2; ++part) w.panel[pn][part] = ws + B.off_panel[pn][part];
+    for (int pn = 0; pn < B.W.n_panels; ++pn) w.panel[pn] = ws + B.off_panel[pn];
     w.part = reinterpret_cast<float*>(ws + B.off_part);
     w.P = B.P;
     w.n_blocks = B.R_pad / 16;

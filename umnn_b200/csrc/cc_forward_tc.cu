@@ -77,13 +77,12 @@ __device__ __forceinline__ float hact(float v) {
     return HIDDEN_ACT == UMNN_ACT_LEAKY_RELU ? fmaxf(v, v * kLeakySlope) : fmaxf(v, 0.0f);
 }
 
-// two 16-byte granules (16 columns) of a bf16 hi / lo panel pair: o[0..7] = hi pairs, o[8..15] = lo pairs
-__device__ __forceinline__ void emit16(uint8_t* hi, uint8_t* lo, long long pr, int col, int W, const uint32_t (&o)[16]) {
-    const size_t g0 = panel_offset(pr, col, W), g1 = panel_offset(pr, col + 8, W);
-    *reinterpret_cast<uint4*>(hi + g0) = make_uint4(o[0], o[1], o[2], o[3]);
-    *reinterpret_cast<uint4*>(hi + g1) = make_uint4(o[4], o[5], o[6], o[7]);
-    *reinterpret_cast<uint4*>(lo + g0) = make_uint4(o[8], o[9], o[10], o[11]);
-    *reinterpret_cast<uint4*>(lo + g1) = make_uint4(o[12], o[13], o[14], o[15]);
+// two 16-byte granules (16 columns) of a bf16 hi / lo panel: o[0..7] = hi pairs, o[8..15] = lo pairs
+__device__ __forceinline__ void emit16(uint8_t* panel, long long pr, int col, int W, const uint32_t (&o)[16]) {
+    *reinterpret_cast<uint4*>(panel + panel_offset(pr, col, W, 0)) = make_uint4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<uint4*>(panel + panel_offset(pr, col + 8, W, 0)) = make_uint4(o[4], o[5], o[6], o[7]);
+    *reinterpret_cast<uint4*>(panel + panel_offset(pr, col, W, 1)) = make_uint4(o[8], o[9], o[10], o[11]);
+    *reinterpret_cast<uint4*>(panel + panel_offset(pr, col + 8, W, 1)) = make_uint4(o[12], o[13], o[14], o[15]);
 }
 
 template <int HIDDEN_ACT, bool EMIT>
@@ -274,9 +273,8 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
                         }
                         split_bf16x2(v2[0], v2[1], hi4[i], lo4[i]);
                     }
-                    const size_t go = panel_offset(pr, gidx * 8, W0);
-                    *reinterpret_cast<uint4*>(p.emit.a_hi[0] + go) = make_uint4(hi4[0], hi4[1], hi4[2], hi4[3]);
-                    *reinterpret_cast<uint4*>(p.emit.a_lo[0] + go) = make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]);
+                    *reinterpret_cast<uint4*>(p.emit.a[0] + panel_offset(pr, gidx * 8, W0, 0)) = make_uint4(hi4[0], hi4[1], hi4[2], hi4[3]);
+                    *reinterpret_cast<uint4*>(p.emit.a[0] + panel_offset(pr, gidx * 8, W0, 1)) = make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]);
                 }
             }
             float* cv = cvec + (size_t)b * p.S.max_slots * L.npad1;
@@ -323,7 +321,7 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
                 if (EMIT) bits |= (a0 > 0.0f ? 1u : 0u) << (2 * i) | (a1 > 0.0f ? 1u : 0u) << (2 * i + 1);
             }
             tmem_st16(tbase + lane_sel + kColQ + 16u * c16, o);
-            if (EMIT) emit16(p.emit.a_hi[1], p.emit.a_lo[1], cta_row0 + (long long)tile * kTcTile + r, 16 * c16, L.npad1, o);
+            if (EMIT) emit16(p.emit.a[1], cta_row0 + (long long)tile * kTcTile + r, 16 * c16, L.npad1, o);
             return bits;
         };
         // publish pair `pp` of MMA layer `m`'s A operand (both CTAs arrive on the leader's barrier)
@@ -374,7 +372,7 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
                         if (EMIT) bits |= (a0 > 0.0f ? 1u : 0u) << (2 * i) | (a1 > 0.0f ? 1u : 0u) << (2 * i + 1);
                     }
                     tmem_st16(taddr, o);
-                    if (EMIT) emit16(p.emit.a_hi[m + 2], p.emit.a_lo[m + 2], pr, 32 * pp, y.npad, o);
+                    if (EMIT) emit16(p.emit.a[m + 2], pr, 32 * pp, y.npad, o);
                     if (two) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -383,7 +381,7 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
                             if (EMIT) bits |= (a0 > 0.0f ? 1u : 0u) << (16 + 2 * i) | (a1 > 0.0f ? 1u : 0u) << (17 + 2 * i);
                         }
                         tmem_st16(taddr + 16, o);
-                        if (EMIT) emit16(p.emit.a_hi[m + 2], p.emit.a_lo[m + 2], pr, 32 * pp + 16, y.npad, o);
+                        if (EMIT) emit16(p.emit.a[m + 2], pr, 32 * pp + 16, y.npad, o);
                     }
                     if (EMIT) p.emit.mask[m + 2][pr * 8 + pp] = bits;
                     publish(m + 1, pp);
@@ -423,7 +421,7 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
                             split_bf16x2(a0, a1, o[i], o[8 + i]);
                             bits |= (a0 > 0.0f ? 1u : 0u) << (2 * i) | (a1 > 0.0f ? 1u : 0u) << (2 * i + 1);
                         }
-                        emit16(p.emit.a_hi[n_mma + 1], p.emit.a_lo[n_mma + 1], pr, 32 * pp, L.npadL, o);
+                        emit16(p.emit.a[n_mma + 1], pr, 32 * pp, L.npadL, o);
                         if (two) {
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
@@ -431,7 +429,7 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
                                 split_bf16x2(a0, a1, o[i], o[8 + i]);
                                 bits |= (a0 > 0.0f ? 1u : 0u) << (16 + 2 * i) | (a1 > 0.0f ? 1u : 0u) << (17 + 2 * i);
                             }
-                            emit16(p.emit.a_hi[n_mma + 1], p.emit.a_lo[n_mma + 1], pr, 32 * pp + 16, L.npadL, o);
+                            emit16(p.emit.a[n_mma + 1], pr, 32 * pp + 16, L.npadL, o);
                         }
                         p.emit.mask[n_mma + 1][pr * 8 + pp] = bits;
                     }

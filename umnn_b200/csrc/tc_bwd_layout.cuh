@@ -8,10 +8,11 @@
 // turns the bias gradient into one more column of the weight-gradient GEMM).  A_0 = [x_row, h_slot, 1, 0..]
 // has width P_0 = round_up(1 + E + 1, 16).
 //
-// A panel of width W stores bf16 values for R_pad rows in blocks of 16 rows, each block being a ready-made
-// MN-major UMMA operand tile: [k8 = (row % 16) / 8][col / 8][row % 8][col % 8]  (128-byte core matrices, one
-// 16-byte granule = 8 consecutive columns of one row).  The pass-W producer therefore moves contiguous
-// blocks with bulk-TMA copies and the MMA descriptors are LBO = (tile_cols/8)*128, SBO = 128.
+// A panel of width W stores bf16 hi AND lo values for R_pad rows in blocks of 16 rows.  In pass W every panel
+// is one operand of one cta_group::2 MMA, whose two CTAs each supply half of the columns, so a block is laid
+// out as  [column half (2)][part hi/lo][k8 = (row % 16) / 8][col8][row % 8][col % 8]:  each CTA fetches its half
+// of a block (hi + lo, 64 * W/2 bytes, contiguous) with ONE bulk-TMA copy and the result is directly a pair of
+// MN-major UMMA operand tiles (128-byte core matrices; LBO = (W/16)*128 between the K halves, SBO = 128).
 #pragma once
 
 #include "tc_layout.cuh"
@@ -21,9 +22,12 @@ namespace umnn {
 constexpr int kBwdMaxHidden = UMNN_MAX_LAYERS - 1;          // J <= 7
 constexpr int kBwdMaxTiles = 8;                             // tiles of 128 rows per CTA and chunk
 
-__host__ __device__ inline size_t panel_offset(long long pr, int c, int W) {
-    return (size_t)(pr >> 4) * (size_t)(32 * W) + (size_t)(((pr >> 3) & 1) * (W >> 3) + (c >> 3)) * 128 +
-           (size_t)(pr & 7) * 16 + (size_t)(c & 7) * 2;
+__host__ __device__ inline size_t panel_offset(long long pr, int c, int W, int part) {
+    const int hw = W >> 1;                       // columns per CTA half (multiple of 8)
+    const int half = c >= hw ? 1 : 0;
+    const int cin = c - half * hw;
+    return (size_t)(pr >> 4) * (size_t)(64 * W) + (size_t)half * (size_t)(64 * hw) + (size_t)part * (size_t)(32 * hw) +
+           (size_t)(((pr >> 3) & 1) * (hw >> 3) + (cin >> 3)) * 128 + (size_t)(pr & 7) * 16 + (size_t)(cin & 7) * 2;
 }
 
 struct TcChainLayer {
@@ -122,10 +126,9 @@ inline TcDgradSmem make_tc_dgrad_smem(const TcDgradLayout& L, int E, int Q) {
 
 // ---- pass W: one accumulator per Linear layer, all resident in TMEM at once -------------------------
 struct TcWgradLayer {
-    int m_width, n_width;       // panel widths of the M operand (256 rows of D over the CTA pair) and N operand
+    int m_width, n_width;       // panel widths of the M operand (D rows, over the CTA pair) and the N operand
     int m_panel, n_panel;       // indices into the panel table
     int tmem_col;               // first accumulator column
-    int n_half;                 // N columns staged per CTA (n_width / 2)
     int swapped;                // 1: D rows = input units (last Linear layer), 0: D rows = output units
     int lin;                    // Linear layer index in the flat vector
     int n_out, n_in, ones_col;  // true dims; column (or row when swapped) that carries the bias gradient
@@ -134,12 +137,10 @@ struct TcWgradLayer {
 struct TcWgradPlan {
     int n_layers;               // = J + 1
     TcWgradLayer layer[UMNN_MAX_LAYERS];
-    int n_panels;               // panel table: A_0..A_J then DZ_1..DZ_{J+1}; each has hi and lo
+    int n_panels;               // panel table: A_0..A_J then DZ_1..DZ_{J+1}
     int panel_width[2 * UMNN_MAX_LAYERS + 2];
-    uint32_t stage_bytes;       // bytes staged per 16-row K block and CTA
-    uint32_t tile_off[2 * UMNN_MAX_LAYERS + 2][2];   // smem offset of panel tile [panel][hi/lo] inside a stage
-    int tile_cols[2 * UMNN_MAX_LAYERS + 2];          // columns staged per CTA for that panel (half or 128)
-    int tile_is_m[2 * UMNN_MAX_LAYERS + 2];
+    uint32_t stage_bytes;       // bytes staged per 16-row K block and CTA (+ slack for the M-tile over-read)
+    uint32_t tile_off[2 * UMNN_MAX_LAYERS + 2];      // smem offset of the panel's tile (hi, then lo) inside a stage
     int tmem_cols_used;
 };
 
@@ -171,26 +172,20 @@ inline bool make_tc_wgrad_plan(const TcDgradLayout& G, TcWgradPlan* W) {
             y.n_panel = panel_DZ(J + 1, J); y.n_width = 16;
             y.ones_col = G.H[J];                // ROW of D (unit H_J of A_J holds 1.0)
         }
-        if (y.m_width > 256 || (y.n_width % 16) != 0) return false;
-        y.n_half = y.n_width / 2;
+        if (y.m_width > 256 || (y.n_width % 16) != 0 || (y.m_width % 16) != 0) return false;
         y.tmem_col = col;
         col += y.n_width;
     }
     W->tmem_cols_used = col;
     if (col > 512) return false;
-    // per-stage tiles: every panel is the M operand of exactly one layer or the N operand of exactly one
-    for (int p = 0; p < W->n_panels; ++p) { W->tile_cols[p] = 0; W->tile_is_m[p] = 0; }
-    for (int l = 0; l < W->n_layers; ++l) {
-        W->tile_cols[W->layer[l].m_panel] = 128;  W->tile_is_m[W->layer[l].m_panel] = 1;
-        W->tile_cols[W->layer[l].n_panel] = W->layer[l].n_half;
-    }
     uint32_t off = 0;
-    for (int p = 0; p < W->n_panels; ++p)
-        for (int part = 0; part < 2; ++part) {
-            W->tile_off[p][part] = off;
-            off += (uint32_t)W->tile_cols[p] * 16 * 2;
-        }
-    W->stage_bytes = off;
+    for (int p = 0; p < W->n_panels; ++p) {
+        W->tile_off[p] = off;
+        off += 32u * (uint32_t)W->panel_width[p];          // hi + lo of half the columns, 16 rows
+    }
+    // an M tile is read as 128 rows per K half although only W/2 are staged: the tensor core over-reads up to
+    // (128 - 8) * 16 bytes past the last K half of the last tile -> keep that much slack inside the stage
+    W->stage_bytes = off + 2048;
     return true;
 }
 

@@ -8,8 +8,7 @@ namespace umnn {
 
 // panels written by pass F (EMIT) for one chunk of rows; index j = hidden layer (0 = network input)
 struct TcEmit {
-    uint8_t* a_hi[UMNN_MAX_LAYERS];
-    uint8_t* a_lo[UMNN_MAX_LAYERS];
+    uint8_t* a[UMNN_MAX_LAYERS];       // A_j panels (bf16 hi and lo interleaved per block, see tc_bwd_layout.cuh)
     uint32_t* mask[UMNN_MAX_LAYERS];   // [R_pad][8] sign bits per 32-column pair, j = 1..J
     float* v;                          // [R_pad] pre-output-activation
     int width[UMNN_MAX_LAYERS];        // panel widths P_j
