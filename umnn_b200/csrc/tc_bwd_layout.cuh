@@ -20,7 +20,7 @@
 namespace umnn {
 
 constexpr int kBwdMaxHidden = UMNN_MAX_LAYERS - 1;          // J <= 7
-constexpr int kBwdMaxTiles = 8;                             // tiles of 128 rows per CTA and chunk
+constexpr int kBwdMaxTiles = 32;                            // tiles of 128 rows per CTA and chunk
 
 __host__ __device__ inline size_t panel_offset(long long pr, int c, int W, int part) {
     const int hw = W >> 1;                       // columns per CTA half (multiple of 8)
