@@ -159,6 +159,26 @@ UMNN_API int umnn_cc_forward_host(const umnn_desc* desc, const float* x0_host, c
                          const float* h_host, const float* flat_params_host, float* out_integral_host,
                          float* out_f_at_x_host, float* out_f_at_x0_host, int32_t device);
 
+/*
+ * Sampling direction: one round of the bracket refinement of UMNNMAF.invert for one dimension
+ * (models/UMNN/UMNNMAF.py:210,213-231; the integral of :213 comes from umnn_cc_forward with
+ * UMNN_LAYOUT_CONTIG over the n_grid * n_samples slots, grid-point major).
+ *   integral, x_grid  [n_grid][n_samples]  integral from 0 to x_grid, and the grid it was taken on
+ *   grid              [n_grid]             relative positions 0 .. 1 (torch.arange(0, 1 + step/2, step))
+ *   offset, target    one float per sample with the given element strides (h[:, j] and z[:, j])
+ *   scale             device pointer to exp(scaling[j])
+ *   left, right       bracket per sample (element stride bracket_stride), updated in place (:229-230)
+ *   x_grid_next       [n_grid][n_samples]  grid of the next round (:210); must not alias x_grid
+ *   x_mid             closest grid point per sample (:231), stride x_mid_stride; may be NULL
+ * With integral == NULL only x_grid_next is laid over the current bracket (first round).
+ * Bit-identical to the reference's torch expressions, including its flat neighbour indexing (:226-227).
+ */
+UMNN_API int umnn_invert_bracket_step(int64_t n_samples, int32_t n_grid, const float* integral, const float* x_grid,
+                             const float* grid, const float* offset, int64_t offset_stride, const float* scale,
+                             const float* target, int64_t target_stride, float* left, float* right,
+                             int64_t bracket_stride, float* x_grid_next, float* x_mid, int64_t x_mid_stride,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -378,6 +378,74 @@ def flow_compute_ll(blocks, x, Q):
 
 
 # ----------------------------------------------------------------------------
+# n3: sampling direction -- UMNNMAF.invert / UMNNMAFFlow.invert
+# ----------------------------------------------------------------------------
+def invert_grid(n_grid: int = 10) -> np.ndarray:
+    """The 10 relative grid positions 0, 1/9, ..., 1 of UMNNMAF.py:183-186 (float32 like torch.arange)."""
+    step = 1.0 / (n_grid - 1)
+    return np.arange(0, 1 + step / 2, step).astype(np.float32)
+
+
+def invert_bracket_step(integ, x_cur, grid, offset, scale, target, left=None, right=None):
+    """One refinement round of UMNNMAF.invert for one dimension, UMNNMAF.py:213-231, float32.
+
+    integ, x_cur [G, B] (integral from 0 to x_cur, grid-point major), offset/target [B], scale a scalar.
+    Returns (left, right, x_next [G, B], x_mid [B]).  Faithful to the reference including the flat
+    neighbour indexing of :226-227: the neighbours of grid point 0 / G-1 are read from the adjacent SAMPLE
+    (index -1 wraps to the last element, the right neighbour wraps modulo B*G).
+    """
+    f32 = np.float32
+    G, B = x_cur.shape
+    z_est = f32(scale) * (offset[None, :].astype(f32) + integ.astype(f32))          # :213
+    diff = np.abs(z_est - target[None, :])
+    pos = np.argmin(diff, axis=0)                                                   # :218 (first minimum)
+    mid = pos + np.arange(B) * G                                                    # :220
+    z_val = z_est.T.reshape(-1)[mid]                                                # :221
+    x_flat = x_cur.T.reshape(-1)                                                    # :222
+    below = (z_val < target).astype(f32)                                            # :224
+    lo = mid - 1                                                                    # :226 (negative wraps)
+    hi = (mid + 1) % x_flat.shape[0]                                                # :227
+    new_left = below * x_flat[mid] + (f32(1) - below) * x_flat[lo]                  # :229
+    new_right = below * x_flat[hi] + (f32(1) - below) * x_flat[mid]                 # :230
+    x_next = grid[:, None] * (new_right - new_left)[None, :] + new_left[None, :]    # :210 of the next round
+    return new_left.astype(f32), new_right.astype(f32), x_next.astype(f32), x_flat[mid].astype(f32)
+
+
+def umnnmaf_invert(blk, z, Q, n_iter=10, n_grid=10):
+    """UMNNMAF.invert, UMNNMAF.py:182-232: per dimension j, `n_iter` rounds of the 10-point bracket
+    refinement on [-50, 50]; every grid evaluation is a contiguous-context integral from 0."""
+    f32 = np.float32
+    B, D = z.shape
+    spec, flat = blk["spec"], blk["flat"]
+    nin, hid, nout, mw = blk["made"]
+    grid = invert_grid(n_grid)
+    x_inv = np.zeros((B, D), f32)
+    for j in range(D):
+        h_all = made_forward(nin, hid, nout, mw, x_inv)                             # :199
+        offset = h_all[:, j]                                                        # :200 (first E-chunk)
+        h_j = h_all[:, j::D]                                                        # :201-202
+        h_rep = np.ascontiguousarray(np.broadcast_to(h_j[None], (n_grid,) + h_j.shape)).reshape(n_grid * B, -1)
+        left = np.full(B, -50, f32)
+        right = np.full(B, 50, f32)
+        x_cur = (grid[:, None] * (right - left)[None, :] + left[None, :]).astype(f32)   # :210
+        x_mid = None
+        for _ in range(n_iter):
+            xs = x_cur.reshape(-1, 1)
+            integ = integrate_parallel(spec, flat, np.zeros_like(xs), xs, h_rep, Q, "contig").reshape(n_grid, B)
+            left, right, x_cur, x_mid = invert_bracket_step(integ, x_cur, grid, offset, 1.0, z[:, j], left, right)
+        x_inv[:, j] = x_mid                                                         # :231
+    return x_inv
+
+
+def flow_invert(blocks, z, Q, n_iter=10):
+    """UMNNMAFFlow.invert, UMNNMAFFlow.py:78-90: blocks in reverse order, feature axis reversed around each."""
+    z = z[:, ::-1]
+    for blk in reversed(blocks):
+        z = umnnmaf_invert(blk, np.ascontiguousarray(z[:, ::-1]), Q, n_iter)
+    return z
+
+
+# ----------------------------------------------------------------------------
 # seeded synthetic data shared by the golden generator, the tests and the bench
 # ----------------------------------------------------------------------------
 def synth_params(spec: MLPSpec, seed: int, gain: float = 1.0) -> np.ndarray:

@@ -447,6 +447,54 @@ def test_flow_compute_ll_on_cuda_matches_reference():
     assert np.max(np.abs(x_back.cpu().numpy() - g["invert_x"])) < 1e-3
 
 
+def test_invert_bracket_step_bit_exact_vs_oracle():
+    """umnn_invert_bracket_step against the numpy restatement of UMNNMAF.py:213-231: bit-exact, including the
+    reference's wrap-around neighbour reads at grid points 0 and G-1."""
+    from umnn_b200 import kernel
+    rng = np.random.RandomState(5)
+    for B, G in ((1, 10), (7, 10), (333, 10), (64, 4)):
+        grid = orc.invert_grid(G)
+        left = rng.uniform(-50, -1, B).astype(np.float32)
+        right = rng.uniform(1, 50, B).astype(np.float32)
+        x_cur = (grid[:, None] * (right - left)[None, :] + left[None, :]).astype(np.float32)
+        integ = np.tanh(x_cur / 10).astype(np.float32) * rng.uniform(0.5, 2, B).astype(np.float32)[None, :]
+        target = rng.uniform(-2.5, 2.5, B).astype(np.float32)      # some targets fall outside the bracket image
+        offset = rng.standard_normal(B).astype(np.float32) * 0.1
+        scale = np.float32(1.25)
+        l_ref, r_ref, xn_ref, xm_ref = orc.invert_bracket_step(integ, x_cur, grid, offset, scale, target)
+        dev = _dev()
+        D = 3                                                       # strided columns like left[:, j]
+        lt = torch.zeros(B, D, device=dev); rt = torch.zeros(B, D, device=dev); xm = torch.zeros(B, D, device=dev)
+        tg = torch.zeros(B, D, device=dev); tg[:, 1] = torch.from_numpy(target).to(dev)
+        lt[:, 1] = torch.from_numpy(left).to(dev); rt[:, 1] = torch.from_numpy(right).to(dev)
+        g_t = torch.from_numpy(grid).to(dev)
+        x0_t = torch.empty(G, B, device=dev)
+        kernel.invert_bracket_step(None, None, g_t, None, None, None, lt[:, 1], rt[:, 1], x0_t, None)
+        assert np.array_equal(x0_t.cpu().numpy(), x_cur)
+        x1_t = torch.empty(G, B, device=dev)
+        kernel.invert_bracket_step(torch.from_numpy(integ).to(dev), x0_t, g_t, torch.from_numpy(offset).to(dev),
+                                   torch.tensor([scale], device=dev), tg[:, 1], lt[:, 1], rt[:, 1], x1_t, xm[:, 1])
+        assert np.array_equal(lt[:, 1].cpu().numpy(), l_ref)
+        assert np.array_equal(rt[:, 1].cpu().numpy(), r_ref)
+        assert np.array_equal(x1_t.cpu().numpy(), xn_ref)
+        assert np.array_equal(xm[:, 1].cpu().numpy(), xm_ref)
+        assert float(lt[:, 0].abs().sum() + lt[:, 2].abs().sum() + xm[:, 0].abs().sum()) == 0.0
+
+
+def test_invert_native_matches_op_by_op_loop(monkeypatch):
+    """The two-launch-per-round invert and the reference-shaped torch loop (same integrals through the same kernel)
+    agree exactly, and both recover x from z = forward(x)."""
+    model, xn, g = _flow_from_golden(_dev())
+    model.eval()
+    z = torch.from_numpy(g["z"][:16].copy()).to(_dev())
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        x_native = model.invert(z, iter=6)
+        monkeypatch.setenv("UMNN_B200_INVERT", "torch")
+        x_loop = model.invert(z, iter=6)
+    assert torch.equal(x_native, x_loop)
+    assert np.max(np.abs(x_native.cpu().numpy() - xn[:16])) < 5e-2
+
+
 def test_monotonic_nn_on_cuda():
     from umnn_b200 import MonotonicNN
     torch.manual_seed(0)
@@ -544,3 +592,54 @@ def test_cuda_graph_capture_and_replay():
     torch.cuda.synchronize()
     want, want_fx, _ = cc_integrate(net, None, x, h, 50, want_fx=True)
     assert torch.equal(out, want) and torch.equal(fx, want_fx)
+
+
+def test_graphed_log_likelihood_replays_and_tracks_parameter_updates():
+    """UMNNMAFFlow.compute_ll captured as one CUDA graph: replays equal the eager call on new
+    inputs, and -- because the parameter packing is captured too -- keep doing so after an in-place update."""
+    from umnn_b200 import GraphedLogLikelihood
+    model, xn, g = _flow_from_golden(_dev())
+    model.eval()
+    B = 8
+    graphed = GraphedLogLikelihood(model, B)
+    x = torch.from_numpy(xn[:B].copy()).to(_dev())
+    ll, z = graphed(x)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ll_e, z_e = model.compute_ll(x)
+    assert torch.equal(ll, ll_e) and torch.equal(z, z_e)
+    ll_first = ll.clone()                       # the graph's outputs are static tensors, rewritten by every replay
+    assert np.max(np.abs(ll.cpu().numpy() - g["ll"][:B])) < 2e-5 * np.max(np.abs(g["ll"]))
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.requires_grad:
+                p.mul_(0.9)
+    x2 = torch.from_numpy(xn[B:2 * B].copy()).to(_dev())
+    ll2, z2 = graphed(x2)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ll2_e, z2_e = model.compute_ll(x2)
+    assert torch.equal(ll2, ll2_e) and torch.equal(z2, z2_e)
+    assert not torch.equal(ll2, ll_first)
+    with pytest.raises(ValueError):
+        graphed(x2[:5])
+
+
+@pytest.mark.parametrize("chunks", [None, 1, 3, 64])
+def test_host_buffer_entry_is_pipelined_and_exact(chunks):
+    """cc_integrate_host (pinned host tensors in and out, copies overlapped with the launches over batch chunks)
+    returns exactly what the resident-input call returns."""
+    from umnn_b200 import cc_integrate, cc_integrate_host
+    spec = orc.MLPSpec((31, 200, 200, 200, 1))
+    net = _net_for(spec, orc.synth_params(spec, 0, 1.0), "strided", 6).eval()
+    gen = torch.Generator(device="cpu").manual_seed(3)
+    x_host = (2 * torch.randn(50, 6, generator=gen)).pin_memory()
+    h_host = torch.randn(50, 180, generator=gen).pin_memory()
+    out, fx = cc_integrate_host(net, x_host, h_host, 50, want_fx=True, chunks=chunks)
+    torch.cuda.synchronize()
+    want, want_fx, _ = cc_integrate(net, None, x_host.to(_dev()), h_host.to(_dev()), 50, want_fx=True)
+    assert torch.equal(out, want.cpu()) and torch.equal(fx, want_fx.cpu())
+    out2, none = cc_integrate_host(net, x_host, h_host, 50, chunks=chunks)
+    torch.cuda.synchronize()
+    want2 = cc_integrate(net, None, x_host.to(_dev()), h_host.to(_dev()), 50)[0]   # rows per slot differ without f(x)
+    assert none is None and torch.equal(out2, want2.cpu())

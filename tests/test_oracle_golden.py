@@ -97,7 +97,7 @@ def test_backward_fp64_matches_finite_differences():
         assert abs(fd - dh[i]) < 1e-6 * max(1.0, abs(fd))
 
 
-def test_flow_compute_ll_matches_reference():
+def _golden_flow():
     g = dict(np.load(os.path.join(GOLDEN_DIR, "flow_ll.npz"), allow_pickle=False))
     D, E, Q, B = (int(v) for v in g["meta"])
     rng = np.random.RandomState(11)
@@ -119,6 +119,38 @@ def test_flow_compute_ll_matches_reference():
                                for j in (0, 2, 4)])
         spec = orc.MLPSpec((1 + E, 50, 50, 1))
         blocks.append(dict(spec=spec, flat=flat, made=(D, hid, D * E, made_w)))
+    return g, blocks, x, Q
+
+
+def test_flow_compute_ll_matches_reference():
+    g, blocks, x, Q = _golden_flow()
     ll, z = orc.flow_compute_ll(blocks, x, Q)
     assert np.max(np.abs(z - g["z"])) < 2e-5 * max(1.0, float(np.max(np.abs(g["z"]))))
     assert np.max(np.abs(ll - g["ll"])) < 2e-5 * max(1.0, float(np.max(np.abs(g["ll"]))))
+
+
+def test_flow_invert_matches_reference():
+    """Sampling direction (UMNNMAFFlow.invert, 5 refinement rounds) against the reference's own output."""
+    g, blocks, x, Q = _golden_flow()
+    x_back = orc.flow_invert(blocks, g["z"][:4].copy(), Q, n_iter=5)
+    assert np.max(np.abs(x_back - g["invert_x"])) < 1e-3
+    assert np.max(np.abs(x_back - g["invert_x_true"])) < 5e-2
+
+
+def test_invert_bracket_step_properties():
+    """The bracket update keeps the closest grid point and its neighbours (UMNNMAF.py:218-230)."""
+    rng = np.random.RandomState(3)
+    G, B = 10, 7
+    grid = orc.invert_grid(G)
+    left = np.full(B, -50, np.float32)
+    right = np.full(B, 50, np.float32)
+    x_cur = grid[:, None] * (right - left)[None, :] + left[None, :]
+    integ = np.tanh(x_cur / 20).astype(np.float32)             # monotone stand-in for the integral
+    target = rng.uniform(-0.7, 0.7, B).astype(np.float32)
+    off = np.zeros(B, np.float32)
+    l, r, x_next, x_mid = orc.invert_bracket_step(integ, x_cur, grid, off, 1.0, target)
+    true_x = 20 * np.arctanh(target)
+    assert np.all(l <= true_x + 1e-4) and np.all(true_x <= r + 1e-4)
+    assert np.allclose(r - l, 100.0 / 9, rtol=1e-5)
+    assert np.allclose(x_next[0], l) and np.allclose(x_next[-1], r, rtol=1e-6)
+    assert np.all(np.abs(x_mid - true_x) <= 100.0 / 9)

@@ -1,7 +1,8 @@
 """umnn_b200: B200-native Clenshaw-Curtis integration hot path of UMNN behind the reference's
 nn.Module / autograd.Function surface.  See DESIGN.md; the C ABI is in include/umnn_b200.h."""
 from .flow import EmbeddingNetwork, MonotonicNN, UMNNMAF, UMNNMAFFlow  # noqa: F401
-from .integral import (NeuralIntegral, ParallelNeuralIntegral, cc_integrate, integrate,  # noqa: F401
+from .graphs import GraphedLogLikelihood  # noqa: F401
+from .integral import (NeuralIntegral, ParallelNeuralIntegral, cc_integrate, cc_integrate_host, integrate,  # noqa: F401
                        integrate_sequential)
 from .networks import (ConditionnalMADE, ContiguousIntegrand, ELUPlus, IntegrandNN, IntegrandNetwork,  # noqa: F401
                        MADE, MaskedLinear)

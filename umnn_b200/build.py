@@ -10,7 +10,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libumnn_b200.so")
-SOURCES = ["umnn_abi.cu", "cc_forward_fp32.cu", "cc_forward_tc.cu", "cc_backward_fp32.cu", "cc_backward_tc.cu"]
+SOURCES = ["umnn_abi.cu", "cc_forward_fp32.cu", "cc_forward_tc.cu", "cc_backward_fp32.cu", "cc_backward_tc.cu", "invert_bracket.cu"]
 HEADERS = ["umnn_common.cuh", "tc_common.cuh", "tc_layout.cuh", "tc_bwd_layout.cuh", "tc_kernels.cuh", os.path.join("..", "..", "include", "umnn_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC,-fvisibility=hidden", "--use_fast_math=false"]

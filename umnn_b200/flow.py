@@ -12,13 +12,15 @@ for CUDA float32 tensors).
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 import torch
 import torch.nn as nn
 
+from . import kernel
 from .integral import (FusedIntegralAndPoint, NeuralIntegral, ParallelNeuralIntegral, fused_point_available,
-                       integral_nograd)
+                       integral_nograd, kernel_route)
 from .networks import (ConditionnalMADE, ContiguousIntegrand, IntegrandNN, IntegrandNetwork, MADE, _flatten, _mlp)
 from .quadrature import compute_cc_weights
 
@@ -181,13 +183,17 @@ class UMNNMAF(nn.Module):
         B, D = z.shape
         dev = self.device
         grid = torch.arange(0, 1 + .5 / (n_grid - 1), 1 / (n_grid - 1)).to(dev)          # [10]
+        derivative = ContiguousIntegrand(self.net.parallel_nets)
+        # UMNN_B200_INVERT=torch keeps the op-by-op loop below on CUDA (benchmarks, A/B checks)
+        if iter >= 1 and B > 0 and z.dtype == torch.float32 and os.environ.get("UMNN_B200_INVERT", "") != "torch" and \
+                kernel_route(derivative, z[:, :1], z[:, :1], z) is not None:
+            return self._invert_native(z, iter, context, derivative, grid)
         target = z.unsqueeze(0).expand(n_grid, -1, -1)                                    # [10, B, D]
         x = target.clone()
         x_inv = torch.zeros(B, D).to(dev)
         left = -50 * torch.ones(B, D).to(dev)
         right = 50 * torch.ones(B, D).to(dev)
         s = torch.exp(self.scaling.unsqueeze(0).unsqueeze(1).expand(n_grid, B, -1))
-        derivative = ContiguousIntegrand(self.net.parallel_nets)
         sample_base = torch.arange(0, B).to(dev) * n_grid
         with torch.no_grad():
             for j in range(self.input_size):
@@ -213,6 +219,37 @@ class UMNNMAF(nn.Module):
                     left[:, j] = below * x_flat[mid] + (1 - below) * x_flat[lo]
                     right[:, j] = below * x_flat[hi] + (1 - below) * x_flat[mid]
                 x_inv[:, j] = x_flat[mid]
+        return x_inv
+
+
+    def _invert_native(self, z, iter, context, derivative, grid):
+        """invert() on the kernel route: per refinement round ONE fused integral launch over the 10*B grid slots
+        (contiguous-context layout) and ONE bracket-update launch (umnn_invert_bracket_step) instead of the
+        ~15 torch ops of UMNNMAF.py:213-231.  Same arithmetic, same results."""
+        n_grid = grid.shape[0]
+        B, D = z.shape
+        dev = z.device
+        spec = derivative.kernel_spec()
+        z = z.contiguous()
+        x_inv = torch.zeros(B, D, device=dev)
+        left = torch.full((B, D), -50., device=dev)
+        right = torch.full((B, D), 50., device=dev)
+        s = torch.exp(self.scaling.detach()).to(dev).float().contiguous()
+        x_a = torch.empty(n_grid, B, device=dev)
+        x_b = torch.empty(n_grid, B, device=dev)
+        with torch.no_grad():
+            for j in range(self.input_size):
+                if j % 100 == 0:
+                    print(j)
+                h_all = self.net.make_embeding(x_inv, context).float()
+                offset = h_all[:, j]
+                h_j = h_all[:, j::D].unsqueeze(0).expand(n_grid, -1, -1).reshape(n_grid * B, -1)
+                kernel.invert_bracket_step(None, None, grid, None, None, None, left[:, j], right[:, j], x_a, None)
+                for _ in range(iter):
+                    integ = kernel.cc_forward(spec, None, x_a.view(-1, 1), h_j, self.nb_steps)[0]
+                    kernel.invert_bracket_step(integ.view(n_grid, B), x_a, grid, offset, s[j:j + 1], z[:, j],
+                                               left[:, j], right[:, j], x_b, x_inv[:, j])
+                    x_a, x_b = x_b, x_a
         return x_inv
 
 

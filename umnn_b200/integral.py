@@ -170,6 +170,8 @@ def kernel_route(integrand, x0, x, h, inv_f=False):
         return None
     if torch.jit.is_tracing() or torch.jit.is_scripting():
         return None
+    if os.environ.get("UMNN_B200_ROUTE", "") == "torch":
+        return None     # measurement knob: the reference's algorithm as torch ops on the same device (never a default)
     get_spec = getattr(integrand, "kernel_spec", None)
     if not callable(get_spec):
         return None
@@ -356,3 +358,70 @@ def cc_integrate(integrand, x0, x, h, nb_steps, want_fx=False, want_fx0=False, p
                          "(IntegrandNetwork, IntegrandNN, ContiguousIntegrand) within the kernel's limits")
     with torch.no_grad():
         return kernel.cc_forward(spec, x0, x, h, nb_steps, want_fx=want_fx, want_fx0=want_fx0, precision=precision)
+
+
+def cc_integrate_host(integrand, x_host, h_host, nb_steps, want_fx=False, out=None, fx_out=None, device=None,
+                      chunks=None, precision=None):
+    """Host-buffer entry of the fused kernel: (pinned) host tensors in, host tensors out -> (integral, f(x,h) | None).
+
+    x0 = 0 as in UMNNMAF.forward (UMNNMAF.py:77).  The batch is cut into `chunks` pieces whose host->device copy,
+    fused launch and device->host copy run on three streams, so only the first piece's upload and the last
+    piece's download are exposed.  Results are complete once the CURRENT stream of `device` is synchronised
+    (the call itself does not block).  `out` / `fx_out`: optional preallocated (pinned) result tensors.
+    """
+    params = _params_of(integrand)
+    if device is None:
+        if not params:
+            raise ValueError("cc_integrate_host: pass device= for a parameter-free integrand")
+        device = params[0].device
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise ValueError("cc_integrate_host needs the integrand on a CUDA device")
+    B = x_host.shape[0]
+    if out is None:
+        out = torch.empty(x_host.shape, dtype=torch.float32, pin_memory=True)
+    if want_fx and fx_out is None:
+        fx_out = torch.empty(x_host.shape, dtype=torch.float32, pin_memory=True)
+    if B == 0:
+        return out, (fx_out if want_fx else None)
+    if chunks is None:
+        chunks = 4 if (x_host.numel() + h_host.numel()) * 4 >= (32 << 20) else 1
+    chunks = max(1, min(int(chunks), B))
+    bounds = [B * c // chunks for c in range(chunks + 1)]
+    main = torch.cuda.current_stream(device)
+    s_in, s_out = _side_streams(device)
+    s_in.wait_stream(main)
+    s_out.wait_stream(main)
+    with torch.no_grad():
+        for c in range(chunks):
+            lo, hi = bounds[c], bounds[c + 1]
+            with torch.cuda.stream(s_in):
+                xd = x_host[lo:hi].to(device, non_blocking=True)
+                hd = h_host[lo:hi].to(device, non_blocking=True)
+            main.wait_stream(s_in)
+            xd.record_stream(main)
+            hd.record_stream(main)
+            spec = kernel_route(integrand, xd, xd, hd, False)
+            if spec is None:
+                raise ValueError("cc_integrate_host needs float32 inputs and a recognised integrand within the "
+                                 "kernel's limits")
+            o, f, _ = kernel.cc_forward(spec, None, xd, hd, nb_steps, want_fx=want_fx, precision=precision)
+            s_out.wait_stream(main)
+            with torch.cuda.stream(s_out):
+                out[lo:hi].copy_(o, non_blocking=True)
+                o.record_stream(s_out)
+                if want_fx:
+                    fx_out[lo:hi].copy_(f, non_blocking=True)
+                    f.record_stream(s_out)
+    main.wait_stream(s_out)
+    return out, (fx_out if want_fx else None)
+
+
+_side = {}
+
+
+def _side_streams(device):
+    key = str(device)
+    if key not in _side:
+        _side[key] = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
+    return _side[key]

@@ -4,6 +4,7 @@ the stream provider here.
 """
 from __future__ import annotations
 
+import contextlib
 import os
 from typing import Optional
 
@@ -29,6 +30,21 @@ def _as_f32c(t: torch.Tensor) -> torch.Tensor:
     return t if (t.is_contiguous() and t.dtype == torch.float32) else t.contiguous().float()
 
 
+_repack_always = False
+
+
+@contextlib.contextmanager
+def repack_every_call():
+    """Inside this context the packed-parameter cache is bypassed, so the (tiny) pack launches are issued on
+    every call -- used while capturing CUDA graphs, whose replays must read the live parameter values."""
+    global _repack_always
+    prev, _repack_always = _repack_always, True
+    try:
+        yield
+    finally:
+        _repack_always = prev
+
+
 def flat_parameters(spec: KernelSpec) -> torch.Tensor:
     return torch.cat([p.detach().reshape(-1) for p in spec.parameters()])
 
@@ -44,7 +60,7 @@ def packed_parameters(spec: KernelSpec, desc: _native.Desc, device: torch.device
     L = _native.lib()
     owner = spec.linears[0]
     stamp = None
-    if not owner.training:
+    if not owner.training and not _repack_always:
         stamp = (desc.precision, str(device)) + tuple((id(p), p.data_ptr(), p._version) for p in spec.parameters())
         hit = owner.__dict__.get("_umnn_packed", {}).get(desc.precision)
         if hit is not None and hit[0] == stamp:
@@ -208,3 +224,33 @@ def cc_backward(spec: KernelSpec, x0: Optional[torch.Tensor], x: torch.Tensor, h
                                          w.data_ptr(), grad_out.data_ptr(), _ptr(grad_fx), _ptr(d_x0), _ptr(d_x),
                                          _ptr(d_h), _ptr(d_flat), ws.data_ptr(), ws_bytes, stream))
     return d_x0, d_x, d_flat, d_h
+
+
+def invert_bracket_step(integ: Optional[torch.Tensor], x_grid: Optional[torch.Tensor], grid: torch.Tensor,
+                        offset: Optional[torch.Tensor], scale: Optional[torch.Tensor], target: Optional[torch.Tensor],
+                        left: torch.Tensor, right: torch.Tensor, x_grid_next: torch.Tensor,
+                        x_mid: Optional[torch.Tensor]) -> None:
+    """One round of UMNNMAF.invert's bracket refinement for one dimension (UMNNMAF.py:210,213-231) as one launch.
+
+    integ, x_grid, x_grid_next: contiguous [G, B]; offset, target, left, right, x_mid: 1-D views of length B (any
+    stride, e.g. columns of [B, D] tensors); scale: 1-element tensor.  integ=None only lays the first grid.
+    left/right/x_mid/x_grid_next are written in place.
+    """
+    L = _native.lib()
+    G, B = x_grid_next.shape
+    for t in (integ, x_grid, x_grid_next, grid):
+        if t is not None and not (t.is_contiguous() and t.dtype == torch.float32):
+            raise ValueError("invert_bracket_step: grids must be contiguous float32")
+    if left.stride(0) != right.stride(0):
+        raise ValueError("invert_bracket_step: left and right must share a stride")
+    dev = x_grid_next.device
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    def stride(t):
+        return 0 if t is None else t.stride(0)
+
+    with torch.cuda.device(dev):
+        _native.check(L.umnn_invert_bracket_step(B, G, _ptr(integ), _ptr(x_grid), grid.data_ptr(), _ptr(offset),
+                                                 stride(offset), _ptr(scale), _ptr(target), stride(target),
+                                                 left.data_ptr(), right.data_ptr(), left.stride(0),
+                                                 x_grid_next.data_ptr(), _ptr(x_mid), stride(x_mid), stream))
