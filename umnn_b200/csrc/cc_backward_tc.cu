@@ -67,17 +67,20 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"r"(kEpiThreads) : "memory"); }
 
-__device__ __forceinline__ void emit16(uint8_t* panel, long long pr, int col, int W, const uint32_t (&o)[16]) {
-    *reinterpret_cast<uint4*>(panel + panel_offset(pr, col, W, 0)) = make_uint4(o[0], o[1], o[2], o[3]);
-    *reinterpret_cast<uint4*>(panel + panel_offset(pr, col + 8, W, 0)) = make_uint4(o[4], o[5], o[6], o[7]);
-    *reinterpret_cast<uint4*>(panel + panel_offset(pr, col, W, 1)) = make_uint4(o[8], o[9], o[10], o[11]);
-    *reinterpret_cast<uint4*>(panel + panel_offset(pr, col + 8, W, 1)) = make_uint4(o[12], o[13], o[14], o[15]);
+__device__ __forceinline__ void emit16(const PanelRow& R, int col, const uint32_t (&o)[16]) {
+    uint8_t* g0 = R.base + panel_granule(R, col);
+    uint8_t* g1 = R.base + panel_granule(R, col + 8);
+    *reinterpret_cast<uint4*>(g0) = make_uint4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<uint4*>(g1) = make_uint4(o[4], o[5], o[6], o[7]);
+    *reinterpret_cast<uint4*>(g0 + R.lo_off) = make_uint4(o[8], o[9], o[10], o[11]);
+    *reinterpret_cast<uint4*>(g1 + R.lo_off) = make_uint4(o[12], o[13], o[14], o[15]);
 }
 
+// v * act'(.) for column c (0..31) of a pair from the recorded sign mask (set bit = negative pre-activation)
 template <int HIDDEN_ACT>
-__device__ __forceinline__ float slope_of(uint32_t bits, int i) {
-    // derivative of the hidden activation from the recorded sign bit of its output
-    return ((bits >> i) & 1u) ? 1.0f : (HIDDEN_ACT == UMNN_ACT_LEAKY_RELU ? kLeakySlope : 0.0f);
+__device__ __forceinline__ float times_slope(float v, uint32_t bits, int c) {
+    if (bits & (1u << mask_bitpos(c))) v = (HIDDEN_ACT == UMNN_ACT_LEAKY_RELU) ? v * kLeakySlope : 0.0f;
+    return v;
 }
 
 template <int HIDDEN_ACT>
@@ -245,17 +248,21 @@ __global__ void __launch_bounds__(kThreads, 1) cc_dgrad_tc_kernel(const __grid_c
             const float dv = dvrow[bu * kTcTile + r];
             const uint32_t bits = p.mask[J][pr * 8 + pp];
             const int halves = (32 * pp + 16 < PJ) ? 2 : 1;
-            for (int hf = 0; hf < halves; ++hf) {
-                const float* wv = wlast + 32 * pp + 16 * hf;
-                uint32_t o[16];
+            const PanelRow prow = panel_row(p.dz[J], pr, PJ);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float z0 = dv * wv[2 * i] * slope_of<HIDDEN_ACT>(bits, 16 * hf + 2 * i);
-                    const float z1 = dv * wv[2 * i + 1] * slope_of<HIDDEN_ACT>(bits, 16 * hf + 2 * i + 1);
-                    split_bf16x2(z0, z1, o[i], o[8 + i]);
+            for (int hf = 0; hf < 2; ++hf) {
+                if (hf < halves) {
+                    const float* wv = wlast + 32 * pp + 16 * hf;
+                    uint32_t o[16];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float z0 = times_slope<HIDDEN_ACT>(dv * wv[2 * i], bits, 16 * hf + 2 * i);
+                        const float z1 = times_slope<HIDDEN_ACT>(dv * wv[2 * i + 1], bits, 16 * hf + 2 * i + 1);
+                        split_bf16x2(z0, z1, o[i], o[8 + i]);
+                    }
+                    tmem_st16(tbase + lane_sel + kColQ + 32u * pp + 16u * hf, o);
+                    emit16(prow, 32 * pp + 16 * hf, o);
                 }
-                tmem_st16(tbase + lane_sel + kColQ + 32u * pp + 16u * hf, o);
-                emit16(p.dz[J], pr, 32 * pp + 16 * hf, PJ, o);
             }
             tmem_st_wait();
             tc_fence_before_sync();
@@ -290,19 +297,20 @@ __global__ void __launch_bounds__(kThreads, 1) cc_dgrad_tc_kernel(const __grid_c
                     tmem_ld16(taddr, v0);
                     if (two) tmem_ld16(taddr + 16, v1);
                     tmem_ld_wait();
+                    const PanelRow prow = panel_row(p.dz[jout], pr, y.npad);
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
-                        split_bf16x2(__uint_as_float(v0[2 * i]) * slope_of<HIDDEN_ACT>(bits, 2 * i),
-                                     __uint_as_float(v0[2 * i + 1]) * slope_of<HIDDEN_ACT>(bits, 2 * i + 1), o[i], o[8 + i]);
+                        split_bf16x2(times_slope<HIDDEN_ACT>(__uint_as_float(v0[2 * i]), bits, 2 * i),
+                                     times_slope<HIDDEN_ACT>(__uint_as_float(v0[2 * i + 1]), bits, 2 * i + 1), o[i], o[8 + i]);
                     tmem_st16(taddr, o);
-                    emit16(p.dz[jout], pr, 32 * pp, y.npad, o);
+                    emit16(prow, 32 * pp, o);
                     if (two) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
-                            split_bf16x2(__uint_as_float(v1[2 * i]) * slope_of<HIDDEN_ACT>(bits, 16 + 2 * i),
-                                         __uint_as_float(v1[2 * i + 1]) * slope_of<HIDDEN_ACT>(bits, 17 + 2 * i), o[i], o[8 + i]);
+                            split_bf16x2(times_slope<HIDDEN_ACT>(__uint_as_float(v1[2 * i]), bits, 16 + 2 * i),
+                                         times_slope<HIDDEN_ACT>(__uint_as_float(v1[2 * i + 1]), bits, 17 + 2 * i), o[i], o[8 + i]);
                         tmem_st16(taddr + 16, o);
-                        emit16(p.dz[jout], pr, 32 * pp + 16, y.npad, o);
+                        emit16(prow, 32 * pp + 16, o);
                     }
                     tmem_st_wait();
                     tc_fence_before_sync();

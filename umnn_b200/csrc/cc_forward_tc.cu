@@ -78,11 +78,13 @@ __device__ __forceinline__ float hact(float v) {
 }
 
 // two 16-byte granules (16 columns) of a bf16 hi / lo panel: o[0..7] = hi pairs, o[8..15] = lo pairs
-__device__ __forceinline__ void emit16(uint8_t* panel, long long pr, int col, int W, const uint32_t (&o)[16]) {
-    *reinterpret_cast<uint4*>(panel + panel_offset(pr, col, W, 0)) = make_uint4(o[0], o[1], o[2], o[3]);
-    *reinterpret_cast<uint4*>(panel + panel_offset(pr, col + 8, W, 0)) = make_uint4(o[4], o[5], o[6], o[7]);
-    *reinterpret_cast<uint4*>(panel + panel_offset(pr, col, W, 1)) = make_uint4(o[8], o[9], o[10], o[11]);
-    *reinterpret_cast<uint4*>(panel + panel_offset(pr, col + 8, W, 1)) = make_uint4(o[12], o[13], o[14], o[15]);
+__device__ __forceinline__ void emit16(const PanelRow& R, int col, const uint32_t (&o)[16]) {
+    uint8_t* g0 = R.base + panel_granule(R, col);
+    uint8_t* g1 = R.base + panel_granule(R, col + 8);
+    *reinterpret_cast<uint4*>(g0) = make_uint4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<uint4*>(g1) = make_uint4(o[4], o[5], o[6], o[7]);
+    *reinterpret_cast<uint4*>(g0 + R.lo_off) = make_uint4(o[8], o[9], o[10], o[11]);
+    *reinterpret_cast<uint4*>(g1 + R.lo_off) = make_uint4(o[12], o[13], o[14], o[15]);
 }
 
 template <int HIDDEN_ACT, bool EMIT>
@@ -311,18 +313,19 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
             const float xn = xnode[bu * kTcTile + r];
             const float* cv = cvec + ((size_t)bu * p.S.max_slots + lsrel[bu * kTcTile + r]) * L.npad1 + 16 * c16;
             const float* wx = w1x + 16 * c16;
-            uint32_t o[16];
-            uint32_t bits = 0;
+            uint32_t o[16], pre[16];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float a0 = hact<HIDDEN_ACT>(fmaf(xn, wx[2 * i], cv[2 * i]));
-                const float a1 = hact<HIDDEN_ACT>(fmaf(xn, wx[2 * i + 1], cv[2 * i + 1]));
-                split_bf16x2(a0, a1, o[i], o[8 + i]);
-                if (EMIT) bits |= (a0 > 0.0f ? 1u : 0u) << (2 * i) | (a1 > 0.0f ? 1u : 0u) << (2 * i + 1);
+                const float v0 = fmaf(xn, wx[2 * i], cv[2 * i]), v1 = fmaf(xn, wx[2 * i + 1], cv[2 * i + 1]);
+                split_bf16x2(hact<HIDDEN_ACT>(v0), hact<HIDDEN_ACT>(v1), o[i], o[8 + i]);
+                if (EMIT) { pre[2 * i] = __float_as_uint(v0); pre[2 * i + 1] = __float_as_uint(v1); }
             }
             tmem_st16(tbase + lane_sel + kColQ + 16u * c16, o);
-            if (EMIT) emit16(p.emit.a[1], cta_row0 + (long long)tile * kTcTile + r, 16 * c16, L.npad1, o);
-            return bits;
+            if (EMIT) {
+                emit16(panel_row(p.emit.a[1], cta_row0 + (long long)tile * kTcTile + r, L.npad1), 16 * c16, o);
+                return sign_mask16(pre);
+            }
+            return 0u;
         };
         // publish pair `pp` of MMA layer `m`'s A operand (both CTAs arrive on the leader's barrier)
         auto publish = [&](int m, int pp) {
@@ -333,7 +336,7 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
         };
         auto l1_pair = [&](int bu, int tile, int pp) {
             uint32_t bits = l1_half(bu, tile, 2 * pp);
-            if (32 * pp + 16 < L.npad1) bits |= l1_half(bu, tile, 2 * pp + 1) << 16;
+            if (32 * pp + 16 < L.npad1) bits |= l1_half(bu, tile, 2 * pp + 1) << 4;
             if (EMIT) p.emit.mask[1][(cta_row0 + (long long)tile * kTcTile + r) * 8 + pp] = bits;
             publish(0, pp);
         };
@@ -364,26 +367,23 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
                     if (two) tmem_ld16(taddr + 16, v1);
                     tmem_ld_wait();
                     const long long pr = cta_row0 + (long long)t * kTcTile + r;
-                    uint32_t bits = 0;
+                    PanelRow prow;
+                    if (EMIT) prow = panel_row(p.emit.a[m + 2], pr, y.npad);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float a0 = hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i])), a1 = hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i + 1]));
-                        split_bf16x2(a0, a1, o[i], o[8 + i]);
-                        if (EMIT) bits |= (a0 > 0.0f ? 1u : 0u) << (2 * i) | (a1 > 0.0f ? 1u : 0u) << (2 * i + 1);
-                    }
+                    for (int i = 0; i < 8; ++i)
+                        split_bf16x2(hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i + 1])),
+                                     o[i], o[8 + i]);
                     tmem_st16(taddr, o);
-                    if (EMIT) emit16(p.emit.a[m + 2], pr, 32 * pp, y.npad, o);
+                    if (EMIT) emit16(prow, 32 * pp, o);
                     if (two) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float a0 = hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i])), a1 = hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i + 1]));
-                            split_bf16x2(a0, a1, o[i], o[8 + i]);
-                            if (EMIT) bits |= (a0 > 0.0f ? 1u : 0u) << (16 + 2 * i) | (a1 > 0.0f ? 1u : 0u) << (17 + 2 * i);
-                        }
+                        for (int i = 0; i < 8; ++i)
+                            split_bf16x2(hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i + 1])),
+                                         o[i], o[8 + i]);
                         tmem_st16(taddr + 16, o);
-                        if (EMIT) emit16(p.emit.a[m + 2], pr, 32 * pp + 16, y.npad, o);
+                        if (EMIT) emit16(prow, 32 * pp + 16, o);
                     }
-                    if (EMIT) p.emit.mask[m + 2][pr * 8 + pp] = bits;
+                    if (EMIT) p.emit.mask[m + 2][pr * 8 + pp] = sign_mask16(v0) | (two ? sign_mask16(v1) << 4 : 0u);
                     publish(m + 1, pp);
                 }
             }
@@ -414,24 +414,21 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
                     if (EMIT) {
                         // last hidden activations a_J (operand of the output layer's weight gradient) and their signs
                         const long long pr = cta_row0 + (long long)t * kTcTile + r;
-                        uint32_t o[16], bits = 0;
+                        const PanelRow prow = panel_row(p.emit.a[n_mma + 1], pr, L.npadL);
+                        uint32_t o[16];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float a0 = hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i])), a1 = hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i + 1]));
-                            split_bf16x2(a0, a1, o[i], o[8 + i]);
-                            bits |= (a0 > 0.0f ? 1u : 0u) << (2 * i) | (a1 > 0.0f ? 1u : 0u) << (2 * i + 1);
-                        }
-                        emit16(p.emit.a[n_mma + 1], pr, 32 * pp, L.npadL, o);
+                        for (int i = 0; i < 8; ++i)
+                            split_bf16x2(hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i + 1])),
+                                         o[i], o[8 + i]);
+                        emit16(prow, 32 * pp, o);
                         if (two) {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float a0 = hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i])), a1 = hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i + 1]));
-                                split_bf16x2(a0, a1, o[i], o[8 + i]);
-                                bits |= (a0 > 0.0f ? 1u : 0u) << (16 + 2 * i) | (a1 > 0.0f ? 1u : 0u) << (17 + 2 * i);
-                            }
-                            emit16(p.emit.a[n_mma + 1], pr, 32 * pp + 16, L.npadL, o);
+                            for (int i = 0; i < 8; ++i)
+                                split_bf16x2(hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i + 1])),
+                                             o[i], o[8 + i]);
+                            emit16(prow, 32 * pp + 16, o);
                         }
-                        p.emit.mask[n_mma + 1][pr * 8 + pp] = bits;
+                        p.emit.mask[n_mma + 1][pr * 8 + pp] = sign_mask16(v0) | (two ? sign_mask16(v1) << 4 : 0u);
                     }
                 } else if (even_layers) {
                     // columns beyond the last accumulator: free once every MMA of this tile is done

@@ -30,6 +30,34 @@ __host__ __device__ inline size_t panel_offset(long long pr, int c, int W, int p
            (size_t)(((pr >> 3) & 1) * (hw >> 3) + (cin >> 3)) * 128 + (size_t)(pr & 7) * 16 + (size_t)(cin & 7) * 2;
 }
 
+// Row-resolved view of a panel for the epilogue threads: everything of panel_offset() that depends on the row
+// is folded into `base` once per tile, leaving 16*c (+ a constant in the second column half) per 8-column granule.
+struct PanelRow {
+    uint8_t* base;
+    uint32_t hw;           // columns per CTA half
+    uint32_t half_off;     // extra offset of the second column half (64*hw - 16*hw)
+    uint32_t lo_off;       // offset of the lo part
+};
+__host__ __device__ inline PanelRow panel_row(uint8_t* panel, long long pr, int W) {
+    PanelRow R;
+    const uint32_t hw = (uint32_t)W >> 1;
+    R.base = panel + (size_t)(pr >> 4) * (size_t)(64 * W) + (size_t)(((uint32_t)(pr >> 3) & 1u) * hw * 16u + ((uint32_t)pr & 7u) * 16u);
+    R.hw = hw;
+    R.half_off = 48u * hw;
+    R.lo_off = 32u * hw;
+    return R;
+}
+// byte offset (from PanelRow::base) of the hi granule holding columns c..c+7 (c a multiple of 8)
+__host__ __device__ inline uint32_t panel_granule(const PanelRow& R, int c) {
+    return 16u * (uint32_t)c + ((uint32_t)c >= R.hw ? R.half_off : 0u);
+}
+
+// Sign masks of a 32-column pair: one 32-bit word per (row, pair).  Column c of the pair (0..31) lives at bit
+// 8*(c % 4) + (c % 16) / 4 + 4*(c / 16): the layout three byte-permutes per four fp32 values produce.  A set bit
+// means the pre-activation is negative (sign bit), i.e. the hidden activation's derivative is its slope; a clear
+// bit means derivative 1 (an exactly-zero pre-activation counts as positive here).
+__host__ __device__ constexpr int mask_bitpos(int c) { return 8 * (c & 3) + ((c & 15) >> 2) + 4 * (c >> 4); }
+
 struct TcChainLayer {
     int kpad, npad;
     int nseg, seg_begin[2], seg_n[2];

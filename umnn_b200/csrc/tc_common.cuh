@@ -250,5 +250,19 @@ __device__ __forceinline__ void split_bf16x2(float even, float odd, uint32_t& hi
     lo = pack_bf16x2(even - he, odd - ho);
 }
 
+// sign bits of 16 fp32 bit patterns, element 4k + j -> bit 8j + k (see mask_bitpos in tc_bwd_layout.cuh):
+// three byte permutes gather the top bytes of four values, one shift + mask drops them into place
+__device__ __forceinline__ uint32_t sign_mask16(const uint32_t (&v)[16]) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t t0 = __byte_perm(v[4 * k], v[4 * k + 1], 0x0073);
+        const uint32_t t1 = __byte_perm(v[4 * k + 2], v[4 * k + 3], 0x0073);
+        const uint32_t g = __byte_perm(t0, t1, 0x5410);
+        m |= (g >> (7 - k)) & (0x01010101u << k);
+    }
+    return m;
+}
+
 }  // namespace tc
 }  // namespace umnn
