@@ -172,6 +172,9 @@ def run_reference(args, cfg, name):
     print(json.dumps(out), flush=True)
 
 
+AUTO_TC_DEFAULT = "bf16x3"   # what UMNN_PREC_AUTO resolves to on the tensor cores (umnn_abi.cu: auto_tc_precision)
+
+
 def torch_route_probe(net, cfg, dev, Bs=256, reps=3):
     """The reference-equivalent PyTorch-CUDA formulation (our torch route = the ParallelNeuralIntegral
     algorithm as torch ops: expand / cat / transpose / Linear / activations / weighted sum) on a sub-batch."""
@@ -258,7 +261,10 @@ def run_ours(args, cfg, name):
                               spec.widths, _native.ACT_LEAKY_RELU if cfg["layout"] == "strided" else _native.ACT_RELU,
                               _native.OUT_ELU_PLUS_1, Q, _native.PREC_BF16X3)
     tc_ok = _native.lib().umnn_packed_params_bytes(probe) > 0
-    use_tc = args.precision == "bf16x3" or (args.precision == "auto" and tc_ok)
+    use_tc = args.precision in ("bf16x3", "fp16x3") or (args.precision == "auto" and tc_ok)
+    # which operand split the tensor-core kernel uses (the library resolves `auto` through UMNN_B200_AUTO_TC)
+    auto_tc = os.environ.get("UMNN_B200_AUTO_TC", AUTO_TC_DEFAULT).lower()
+    split = args.precision if args.precision != "auto" else auto_tc
     pad = lambda w: (w + 2 + 15) // 16 * 16
     issued_per_row = 3 * 2 * sum(pad(a) * pad(b) for a, b in zip(spec.widths[1:-2], spec.widths[2:-1])) if use_tc else 0
     net = IntegrandNetwork(D, 1 + E, cfg["hidden"], 1) if cfg["layout"] == "strided" else IntegrandNN(1 + E, cfg["hidden"])
@@ -356,7 +362,8 @@ def run_ours(args, cfg, name):
     out = {
         "metric": "integrand-evals/sec (B*D*Q)", "value": value, "unit": "integrand-evals/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3 (hi+lo split, fp32 accumulate)" if use_tc else "f32",
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": f"{split} (16-bit hi+lo operand split, fp32 accumulate)" if use_tc else "f32",
         "data": "synthetic",
         "config": {"workload": f"{name}: {cfg['label']}", "per_gpu_batch": B, "global_batch": B * world, "D": D,
                    "E": E, "Q": Q, "hidden": cfg["hidden"], "parallelism": f"batch-shard x{world}, no collective",
@@ -369,7 +376,8 @@ def run_ours(args, cfg, name):
                 "d2h_bytes_per_step": int((out_host.numel() + fx_host.numel()) * 4),
                 "api": "umnn_b200.cc_integrate_host on pinned host tensors (H2D + fused kernel + D2H every step, "
                        "pipelined over batch chunks)"},
-        "gpu_launches": args.steps * world,
+        # fp16x3: the fused kernel + its guarded bf16 re-run (a no-op launch unless an activation left the fp16 range)
+        "gpu_launches": args.steps * world * (2 if (use_tc and split == "fp16x3") else 1),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved_tflops / peak, "traffic": traffic,
@@ -402,7 +410,7 @@ def main():
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (debugging only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
-    ap.add_argument("--precision", default=os.environ.get("UMNN_B200_PRECISION", "auto"), choices=["auto", "fp32", "bf16x3"],
+    ap.add_argument("--precision", default=os.environ.get("UMNN_B200_PRECISION", "auto"), choices=["auto", "fp32", "bf16x3", "fp16x3"],
                     help="kernel family: auto = BF16x3 tensor cores when the shape fits, else FP32 FFMA")
     args = ap.parse_args()
     os.environ["UMNN_B200_PRECISION"] = args.precision

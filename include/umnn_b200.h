@@ -53,7 +53,7 @@ extern "C" {
 enum { UMNN_LAYOUT_STRIDED_D = 0, UMNN_LAYOUT_CONTIG = 1 };
 enum { UMNN_ACT_RELU = 0, UMNN_ACT_LEAKY_RELU = 1 };           /* hidden; leaky slope 0.01 */
 enum { UMNN_OUT_ELU_PLUS_1 = 0, UMNN_OUT_SIGMOID = 1 };        /* UMNNMAF.py:11-19 */
-enum { UMNN_PREC_FP32 = 0, UMNN_PREC_BF16X3 = 1, UMNN_PREC_AUTO = 2 };
+enum { UMNN_PREC_FP32 = 0, UMNN_PREC_BF16X3 = 1, UMNN_PREC_AUTO = 2, UMNN_PREC_FP16X3 = 3 };
 
 enum {
     UMNN_ERR_NULL = -1,        /* required pointer is NULL */

@@ -20,6 +20,9 @@ CASES = {
     "cfg1": (100, 1, 2, [64, 64, 64], 50, "contig", 1.0, True, True),
     "odd1": (37, 3, 1, [20, 20], 40, "strided", 1.5, False, True),
     "q200": (9, 5, 4, [48, 32, 16], 200, "strided", 1.5, False, True),
+    "cfg2_trained": (10000, 2, 10, [100, 100, 100, 100], 50, "strided", 2.5, False, True),
+    "cfg5_trained": (100, 784, 30, [100, 50, 50, 50, 50], 50, "strided", 2.5, False, True),
+    "cfg3_trained": (10000, 6, 30, [200, 200, 200], 50, "strided", 2.5, False, True),
 }
 
 
@@ -40,14 +43,18 @@ def run_case(name):
             p.copy_(torch.from_numpy(flat[off:off + p.numel()].copy()).view_as(p))
             off += p.numel()
     dev = torch.device("cuda:0")
-    net.to(dev)
+    net.to(dev).eval()   # packed parameters cached: the timing loop is kernel launches only
     xd, hd, x0d = torch.from_numpy(x).to(dev), torch.from_numpy(h).to(dev), torch.from_numpy(x0).to(dev)
     res = {}
-    for pname, prec in (("fp32", _native.PREC_FP32), ("bf16x3", _native.PREC_BF16X3)):
+    variants = (("fp32", _native.PREC_FP32, "1"), ("bf16x3", _native.PREC_BF16X3, "1"),
+                ("bf16x3-wide", _native.PREC_BF16X3, "0"), ("fp16x3", _native.PREC_FP16X3, "1"),
+                ("fp16x3-wide", _native.PREC_FP16X3, "0"))
+    for pname, prec, narrow in variants:
+        os.environ["UMNN_B200_TC_NARROW"] = narrow     # read by the launcher on every call
         out, fx, fx0 = cc_integrate(net, x0d, xd, hd, Q, want_fx=want_f, want_fx0=want_f, precision=prec)
         torch.cuda.synchronize()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 3
+        reps = 5
         s.record()
         for _ in range(reps):
             cc_integrate(net, x0d, xd, hd, Q, want_fx=want_f, want_fx0=want_f, precision=prec)
@@ -61,13 +68,15 @@ def run_case(name):
     def rel(a, b):
         return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-6)))
     line = f"{name}: "
-    for pname in ("fp32", "bf16x3"):
+    for pname, _, _ in variants:
         o, fx, fx0, ms = res[pname]
         line += f"[{pname} {ms:.3f} ms rel_int={rel(o[:n_chk], ref):.2e}"
         if fx is not None:
             line += f" rel_fx={rel(fx[:n_chk], rfx):.2e} rel_fx0={rel(fx0[:n_chk], rfx0):.2e}"
         line += "] "
-    line += f"tc_vs_fp32_all={rel(res['bf16x3'][0], res['fp32'][0]):.2e} speedup={res['fp32'][3] / res['bf16x3'][3]:.2f}x"
+    line += (f"bf16x3_vs_fp32_all={rel(res['bf16x3'][0], res['fp32'][0]):.2e} "
+             f"fp16x3_vs_fp32_all={rel(res['fp16x3'][0], res['fp32'][0]):.2e} "
+             f"speedup={res['fp32'][3] / res['bf16x3'][3]:.2f}x narrow_gain={res['bf16x3-wide'][3] / res['bf16x3'][3]:.2f}x")
     print(line, flush=True)
 
 

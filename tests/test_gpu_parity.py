@@ -27,16 +27,18 @@ GRAD_TOL = 1e-3
 # cancellation) measure 1e-5..2e-5, so those cases are held to 5e-5 in BF16x3 mode and to 1e-5 in FP32 mode.
 TC_STRESS_TOL = 5e-5
 
-PRECISIONS = ["fp32", "auto"]
+PRECISIONS = ["fp32", "auto", "fp16x3"]
 
 
 def _prec(name):
     from umnn_b200 import _native
-    return {"fp32": _native.PREC_FP32, "bf16x3": _native.PREC_BF16X3, "auto": _native.PREC_AUTO}[name]
+    return {"fp32": _native.PREC_FP32, "bf16x3": _native.PREC_BF16X3, "auto": _native.PREC_AUTO,
+            "fp16x3": _native.PREC_FP16X3}[name]
 
 
 def _tol(precision, gain=1.0):
-    return INTEGRAL_TOL if (precision == "fp32" or gain == 1.0) else TC_STRESS_TOL
+    # FP16x3 (fp16 hi + lo operands, 22 bits) holds the north-star tolerance on the stress networks too
+    return INTEGRAL_TOL if (precision in ("fp32", "fp16x3") or gain == 1.0) else TC_STRESS_TOL
 
 
 def _dev():
@@ -200,6 +202,29 @@ def test_deterministic_and_batch_invariant(precision):
     np.testing.assert_array_equal(a, b)
     c, _, _ = _run_kernel(spec, flat, x0[100:200], x[100:200], h[100:200], 50, "strided", precision=precision)
     assert rel_err(c, a[100:200]) < 2e-6
+
+
+def test_fp16x3_overflow_is_caught_by_the_guarded_rerun():
+    """Activations beyond the fp16 range (|a| > 65504) turn the fp16 attempt into NaN; the flag it raises makes the
+    second (bf16) launch recompute the call, so the result is bit-identical to BF16X3 and finite."""
+    spec = orc.MLPSpec((31, 200, 200, 200, 1))
+    flat = orc.synth_params(spec, 0, 1.0)
+    x0, x, h, _ = orc.synth_inputs(64, 6, 180, 2, x0_zero=True)
+    x = (x * 3.0e6).astype(np.float32)
+    a, fa, _ = _run_kernel(spec, flat, x0, x, h, 50, "strided", precision="fp16x3")
+    b, fb, _ = _run_kernel(spec, flat, x0, x, h, 50, "strided", precision="bf16x3")
+    assert np.all(np.isfinite(a)) and np.all(np.isfinite(fa))
+    np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(fa, fb)
+    ref, _, _ = c_binding.cc_forward(spec, flat, x0, x, h, 50)
+    assert rel_err(a, ref) < 1e-4
+    # in range: the re-run stays a no-op and the fp16 result stands (differs from bf16 in the last bits)
+    x_small = (x / 3.0e6).astype(np.float32)
+    c, _, _ = _run_kernel(spec, flat, x0, x_small, h, 50, "strided", precision="fp16x3")
+    d, _, _ = _run_kernel(spec, flat, x0, x_small, h, 50, "strided", precision="bf16x3")
+    assert not np.array_equal(c, d)
+    ref, _, _ = c_binding.cc_forward(spec, flat, x0, x_small, h, 50)
+    assert rel_err(c, ref) < 2e-6
 
 
 def test_packed_parameter_cache_tracks_updates():

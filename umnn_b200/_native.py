@@ -20,7 +20,7 @@ UMNN_MAX_STEPS = 1024
 LAYOUT_STRIDED_D, LAYOUT_CONTIG = 0, 1
 ACT_RELU, ACT_LEAKY_RELU = 0, 1
 OUT_ELU_PLUS_1, OUT_SIGMOID = 0, 1
-PREC_FP32, PREC_BF16X3, PREC_AUTO = 0, 1, 2
+PREC_FP32, PREC_BF16X3, PREC_AUTO, PREC_FP16X3 = 0, 1, 2, 3
 
 EXPORTS = ("umnn_abi_version", "umnn_last_error", "umnn_cc_tables", "umnn_param_count",
            "umnn_packed_params_bytes", "umnn_pack_params", "umnn_workspace_bytes", "umnn_cc_forward",

@@ -734,7 +734,7 @@ int launch_pack_backward_tc(const umnn_desc* d, const float* flat, void* packed,
     BwdTcPlan B;
     const char* why = make_bwd_plan(d, &B);
     if (why) { set_error("BF16X3 backward: %s", why); return UMNN_ERR_UNSUPPORTED; }
-    int rc = launch_pack_tc(d, flat, packed, s);            // forward blobs first
+    int rc = launch_pack_tc(d, flat, packed, UMNN_OPF_BF16, s);   // forward blobs first
     if (rc) return rc;
     uint8_t* g = (uint8_t*)packed + 2 * (size_t)B.F.blob_bytes;
     const uint32_t n_w = B.G.weights_bytes;

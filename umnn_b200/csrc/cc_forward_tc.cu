@@ -33,14 +33,26 @@ namespace {
 
 using namespace tc;
 
-constexpr int kEpiWarps = 16;                       // 4 per TMEM lane quadrant
-constexpr int kColGroups = kEpiWarps / 4;           // column groups: warp/4 handles 32-column pairs p % 4 == warp/4
-constexpr int kPrepWarps = 3;
-constexpr int kMmaWarp = kEpiWarps + kPrepWarps;
-constexpr int kThreads = (kMmaWarp + 1) * 32;       // 640
-constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kPrepThreads = kPrepWarps * 32;
-constexpr uint32_t kColP = 0, kColQ = kTcRegionCols;
+// Kernel shape.
+//   WIDE    one CTA per SM, 16 epilogue warps, TMEM regions of 256 columns (hidden widths <= 254).
+//   NARROW  two CTAs per SM (two CTA pairs per SM pair), 8 epilogue warps each, TMEM regions of 128 columns
+//           (hidden widths <= 126).  At narrow widths the MMA -> epilogue -> MMA chain of one tile is latency
+//           bound (an MMA layer lasts ~0.6 us, an epilogue stage ~1.7 us), so a second resident tile fills the
+//           tensor pipe while the first one converts.
+template <bool NARROW>
+struct Shape {
+    static constexpr int kEpiWarps = NARROW ? 8 : 16;        // 2 or 4 per TMEM lane quadrant
+    static constexpr int kColGroups = kEpiWarps / 4;         // warp/4 handles 32-column pairs p % kColGroups == warp/4
+    static constexpr int kPrepWarps = 3;
+    static constexpr int kMmaWarp = kEpiWarps + kPrepWarps;
+    static constexpr int kThreads = (kMmaWarp + 1) * 32;     // 640 / 384
+    static constexpr int kEpiThreads = kEpiWarps * 32;
+    static constexpr int kPrepThreads = kPrepWarps * 32;
+    static constexpr uint32_t kRegion = NARROW ? kTcNarrowRegionCols : kTcRegionCols;
+    static constexpr uint32_t kColP = 0, kColQ = kRegion;
+    static constexpr uint32_t kTmemCols = 2 * kRegion;
+    static constexpr int kCtasPerSm = NARROW ? 2 : 1;
+};
 
 // barrier indices
 constexpr int BAR_READY = 0;                                   // [layer][8]  A-operand pair p of MMA layer m is in TMEM
@@ -58,8 +70,10 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  : "memory");
 }
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"r"(kEpiThreads) : "memory"); }
-__device__ __forceinline__ void prep_bar_sync() { asm volatile("bar.sync 2, %0;" ::"r"(kPrepThreads) : "memory"); }
+template <int N_THREADS>
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(N_THREADS) : "memory"); }
+template <int N_THREADS>
+__device__ __forceinline__ void prep_bar_sync() { asm volatile("bar.sync 2, %0;" ::"n"(N_THREADS) : "memory"); }
 
 __device__ __forceinline__ const float* slot_ctx(const TcParams& p, long long slot, int* stride) {
     if (p.layout == UMNN_LAYOUT_STRIDED_D) {
@@ -87,8 +101,16 @@ __device__ __forceinline__ void emit16(const PanelRow& R, int col, const uint32_
     *reinterpret_cast<uint4*>(g1 + R.lo_off) = make_uint4(o[12], o[13], o[14], o[15]);
 }
 
-template <int HIDDEN_ACT, bool EMIT>
-__global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
+template <int HIDDEN_ACT, bool EMIT, bool NARROW, int OPF>
+__global__ void __launch_bounds__(Shape<NARROW>::kThreads, Shape<NARROW>::kCtasPerSm)
+cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
+    using C = Shape<NARROW>;
+    constexpr int kEpiWarps = C::kEpiWarps, kColGroups = C::kColGroups, kPrepWarps = C::kPrepWarps;
+    constexpr int kMmaWarp = C::kMmaWarp, kThreads = C::kThreads, kEpiThreads = C::kEpiThreads, kPrepThreads = C::kPrepThreads;
+    constexpr uint32_t kColP = C::kColP, kColQ = C::kColQ;
+    static_assert(!(EMIT && (NARROW || OPF != UMNN_OPF_BF16)), "pass F runs the wide bf16 shape");
+    // guarded re-run (see launch_forward_tc): nothing to do unless the first attempt raised the flag
+    if (p.run_if != nullptr && *p.run_if == 0) return;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
 
@@ -132,7 +154,7 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
         mbar_init(&bars[BAR_PEER], 2);
         fence_mbar_init();
     }
-    if (warp == kMmaWarp) tmem_alloc<2>(holder, 512);
+    if (warp == kMmaWarp) tmem_alloc<2>(holder, C::kTmemCols);
     for (int i = tid; i <= p.Q; i += kThreads) {
         tab_t[i] = p.nodes[i];
         tab_w[i] = p.weights[i];
@@ -142,6 +164,16 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
     cluster_sync_all();
     tc_fence_after_sync();
     const uint32_t tbase = *holder;
+    if (NARROW && tid == 0) {
+        // two CTA pairs share an SM pair here: the pair-collective allocation must have handed both CTAs of THIS
+        // pair the same columns (one tcgen05.mma addresses the tensor memory of both)
+        uint32_t peer_base;
+        asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(peer_base) : "r"(map_to_cta(smem_u32(holder), rank ^ 1u)) : "memory");
+        if (peer_base != tbase) {
+            printf("cc_forward_tc: tensor-memory base differs inside CTA pair (block %d: %u vs %u)\n", (int)blockIdx.x, tbase, peer_base);
+            __trap();
+        }
+    }
 
     if (warp == kMmaWarp) {
         // =========================================================== MMA issuer warp
@@ -172,7 +204,7 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
                     const int n_kb = y.kpad / 16;
                     uint64_t* ready = &bars[BAR_READY + m * 8];
                     for (int s = 0; s < y.nseg; ++s) {
-                        const uint32_t idesc = make_idesc_bf16_f32(256, y.seg_n[s]);
+                        const uint32_t idesc = make_idesc_f32(256, y.seg_n[s], OPF, OPF);
                         const uint32_t lbo = (uint32_t)(y.seg_n[s] / 16) * 128u;
                         const uint64_t step = (uint64_t)((2u * lbo) >> 4);        // descriptor address field is in 16-byte units
                         const uint32_t d_addr = tbase + col_d + (uint32_t)y.seg_begin[s];
@@ -248,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
                 lsrel[b * kTcTile + r] = rel;
                 nodeid[b * kTcTile + r] = node;
             }
-            prep_bar_sync();
+            prep_bar_sync<kPrepThreads>();
             if (EMIT) {
                 // A_0 = [x_row, h_slot, 1, 0...] as bf16 hi / lo (operand of the first layer's weight gradient)
                 const int W0 = p.emit.width[0];
@@ -289,7 +321,7 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
                 }
                 cv[i * L.npad1 + n] = acc;
             }
-            prep_bar_sync();   // hbuf is rewritten by the next tile
+            prep_bar_sync<kPrepThreads>();   // hbuf is rewritten by the next tile
             if (lane == 0) mbar_arrive(&bars[BAR_PREP_FULL + b]);
         }
     } else {
@@ -317,7 +349,7 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float v0 = fmaf(xn, wx[2 * i], cv[2 * i]), v1 = fmaf(xn, wx[2 * i + 1], cv[2 * i + 1]);
-                split_bf16x2(hact<HIDDEN_ACT>(v0), hact<HIDDEN_ACT>(v1), o[i], o[8 + i]);
+                split_x2<OPF>(hact<HIDDEN_ACT>(v0), hact<HIDDEN_ACT>(v1), o[i], o[8 + i]);
                 if (EMIT) { pre[2 * i] = __float_as_uint(v0); pre[2 * i + 1] = __float_as_uint(v1); }
             }
             tmem_st16(tbase + lane_sel + kColQ + 16u * c16, o);
@@ -371,14 +403,14 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
                     if (EMIT) prow = panel_row(p.emit.a[m + 2], pr, y.npad);
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
-                        split_bf16x2(hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i + 1])),
+                        split_x2<OPF>(hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i + 1])),
                                      o[i], o[8 + i]);
                     tmem_st16(taddr, o);
                     if (EMIT) emit16(prow, 32 * pp, o);
                     if (two) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
-                            split_bf16x2(hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i + 1])),
+                            split_x2<OPF>(hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i + 1])),
                                          o[i], o[8 + i]);
                         tmem_st16(taddr + 16, o);
                         if (EMIT) emit16(prow, 32 * pp + 16, o);
@@ -418,13 +450,13 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
                         uint32_t o[16];
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
-                            split_bf16x2(hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i + 1])),
+                            split_x2<OPF>(hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i + 1])),
                                          o[i], o[8 + i]);
                         emit16(prow, 32 * pp, o);
                         if (two) {
 #pragma unroll
                             for (int i = 0; i < 8; ++i)
-                                split_bf16x2(hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i + 1])),
+                                split_x2<OPF>(hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i + 1])),
                                              o[i], o[8 + i]);
                             emit16(prow, 32 * pp + 16, o);
                         }
@@ -440,7 +472,7 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
 
             // ---- finalize the rows of this tile
             if (cg > 0) part[(cg - 1) * kTcTile + r] = partial;
-            epi_bar_sync();
+            epi_bar_sync<kEpiThreads>();
             if (!even_layers && has_next) {
                 // odd layer counts: the last accumulator lives in P, which MMA layer 0 of the next tile
                 // overwrites -> publish layer 1 of the next tile only after every warp has read P
@@ -452,9 +484,14 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
             const long long row0 = (long long)t * kTcTile;
             if (cg == 0) {
                 const int node = nodeid[b * kTcTile + r];
-                const float vtot = ((partial + part[r]) + part[kTcTile + r]) + part[2 * kTcTile + r];
+                float vtot = partial;
+#pragma unroll
+                for (int g = 1; g < kColGroups; ++g) vtot += part[(g - 1) * kTcTile + r];
                 if (EMIT) p.emit.v[cta_row0 + row0 + r] = node >= 0 ? vtot : 0.0f;
                 if (node >= 0) {
+                    // an fp16 operand that overflowed (|activation| > 65504) has turned every downstream unit
+                    // into NaN: ask for the bf16 re-run
+                    if (OPF == UMNN_OPF_FP16 && p.raise_flag != nullptr && !(fabsf(vtot) <= 3.0e38f)) *p.raise_flag = 1;
                     const float f = out_act(vtot, p.out_act);
                     if (node <= p.Q) {
                         fval[r] = f * tab_w[node];
@@ -465,7 +502,7 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
                     }
                 }
             }
-            epi_bar_sync();
+            epi_bar_sync<kEpiThreads>();
             if (!EMIT && warp == 0 && row0 < n_rows) {
                 const long long last_row = (row0 + kTcTile < n_rows ? row0 + kTcTile : n_rows) - 1;
                 const long long s_first = row0 / p.rps, s_last = last_row / p.rps;
@@ -502,18 +539,22 @@ __global__ void __launch_bounds__(kThreads, 1) cc_forward_tc_kernel(const __grid
     tc_fence_before_sync();
     __syncthreads();
     cluster_sync_all();
-    if (warp == kMmaWarp) tmem_dealloc<2>(tbase, 512);
+    if (warp == kMmaWarp) tmem_dealloc<2>(tbase, C::kTmemCols);
 }
 
 // ---------------------------------------------------------------------------------------------
 // parameter packing
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint16_t bf16_bits(float v) {
-    return (uint16_t)(pack_bf16x2(v, 0.0f) & 0xFFFFu);
+// 16-bit operand encodings (opf = UMNN_OPF_BF16 / UMNN_OPF_FP16) and their fp32 values
+__device__ __forceinline__ uint16_t op_bits(float v, int opf) {
+    return (uint16_t)((opf == UMNN_OPF_BF16 ? pack_bf16x2(v, 0.0f) : pack_f16x2(v, 0.0f)) & 0xFFFFu);
 }
-__device__ __forceinline__ float bf16_val(float v) { return __uint_as_float((uint32_t)bf16_bits(v) << 16); }
+__device__ __forceinline__ float op_val(float v, int opf) {
+    const uint16_t b = op_bits(v, opf);
+    return opf == UMNN_OPF_BF16 ? __uint_as_float((uint32_t)b << 16) : __half2float(__ushort_as_half(b));
+}
 
-__global__ void pack_tc_weights_kernel(const float* __restrict__ flat, uint8_t* __restrict__ blobs, TcLayout L) {
+__global__ void pack_tc_weights_kernel(const float* __restrict__ flat, uint8_t* __restrict__ blobs, TcLayout L, int opf) {
     const uint32_t per_rank = L.weights_bytes / 2;  // bf16 elements
     const uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
     if (gi >= 2 * per_rank) return;
@@ -546,19 +587,19 @@ __global__ void pack_tc_weights_kernel(const float* __restrict__ flat, uint8_t* 
     if (n < y.h_out) {
         if (k < y.h_in) {
             const float w = flat[L.src_w_off[lin] + n * y.h_in + k];
-            hi = bf16_val(w);
-            lo = bf16_val(w - hi);
+            hi = op_val(w, opf);
+            lo = op_val(w - hi, opf);
         } else if (k == y.h_in || k == y.h_in + 1) {
             const float bv = flat[L.src_b_off[lin] + n];
-            const float b_hi = bf16_val(bv);
-            const float b_lo = bf16_val(bv - b_hi);
+            const float b_hi = op_val(bv, opf);
+            const float b_lo = op_val(bv - b_hi, opf);
             if (k == y.h_in) { hi = b_hi; lo = b_lo; }
-            else { hi = bf16_val(bv - b_hi - b_lo); lo = 0.0f; }
+            else { hi = op_val(bv - b_hi - b_lo, opf); lo = 0.0f; }
         }
     } else if ((n == y.h_out && k == y.h_in) || (n == y.h_out + 1 && k == y.h_in + 1)) {
         hi = 1.0f;   // bias carriers propagate the constant 1
     }
-    reinterpret_cast<uint16_t*>(blobs + (size_t)rank * L.blob_bytes)[byte_off / 2] = bf16_bits(part == 0 ? hi : lo);
+    reinterpret_cast<uint16_t*>(blobs + (size_t)rank * L.blob_bytes)[byte_off / 2] = op_bits(part == 0 ? hi : lo, opf);
 }
 
 __global__ void pack_tc_consts_kernel(const float* __restrict__ flat, uint8_t* __restrict__ blobs, TcLayout L, int n_layers) {
@@ -593,6 +634,32 @@ bool tc_two_segments() {
     return !(e && e[0] == '1');
 }
 
+bool tc_narrow_enabled() {
+    const char* e = getenv("UMNN_B200_TC_NARROW");
+    return !(e && e[0] == '0');
+}
+
+template <bool EMIT, bool NARROW, int OPF>
+int launch_tc_kernel(int hidden_act, const TcParams& p, int n_cta, cudaStream_t s) {
+    auto kern = hidden_act == UMNN_ACT_LEAKY_RELU ? cc_forward_tc_kernel<UMNN_ACT_LEAKY_RELU, EMIT, NARROW, OPF>
+                                                  : cc_forward_tc_kernel<UMNN_ACT_RELU, EMIT, NARROW, OPF>;
+    UMNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.S.total));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)n_cta);
+    cfg.blockDim = dim3(Shape<NARROW>::kThreads);
+    cfg.dynamicSmemBytes = p.S.total;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    UMNN_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
+    return 0;
+}
+
 }  // namespace
 
 const char* tc_unsupported_reason(const umnn_desc* d, int extra_rows) {
@@ -604,14 +671,14 @@ const char* tc_unsupported_reason(const umnn_desc* d, int extra_rows) {
     return nullptr;
 }
 
-int launch_pack_tc(const umnn_desc* d, const float* flat, void* packed, cudaStream_t s) {
+int launch_pack_tc(const umnn_desc* d, const float* flat, void* packed, int opf, cudaStream_t s) {
     TcLayout L;
     if (!make_tc_layout(d, &L, tc_two_segments())) {
         set_error("BF16X3: shape not supported by the tensor-core kernel");
         return UMNN_ERR_UNSUPPORTED;
     }
     const uint32_t n_w = L.weights_bytes;  // = 2 ranks x weights_bytes/2 elements
-    pack_tc_weights_kernel<<<(n_w + 255) / 256, 256, 0, s>>>(flat, (uint8_t*)packed, L);
+    pack_tc_weights_kernel<<<(n_w + 255) / 256, 256, 0, s>>>(flat, (uint8_t*)packed, L, opf);
     UMNN_CUDA_TRY(cudaGetLastError());
     const uint32_t n_f = (L.blob_bytes - L.weights_bytes) / 4;
     pack_tc_consts_kernel<<<(n_f + 255) / 256, 256, 0, s>>>(flat, (uint8_t*)packed, L, d->n_layers);
@@ -627,14 +694,15 @@ size_t tc_packed_bytes(const umnn_desc* d) {
 
 int launch_forward_tc(const umnn_desc* d, const float* x0, const float* x, const float* h, const void* packed,
                       const float* nodes, const float* weights, float* out, float* out_fx, float* out_fx0,
-                      cudaStream_t s) {
+                      int opf, const int* run_if, int* raise_flag, cudaStream_t s) {
     TcParams p{};
     if (!make_tc_layout(d, &p.L, tc_two_segments())) {
-        set_error("BF16X3: shape not supported by the tensor-core kernel");
+        set_error("tensor-core forward: shape not supported");
         return UMNN_ERR_UNSUPPORTED;
     }
     p.x0 = x0; p.x = x; p.h = h; p.nodes = nodes; p.weights = weights; p.blobs = (const uint8_t*)packed;
     p.out = out; p.out_fx = out_fx; p.out_fx0 = out_fx0;
+    p.run_if = run_if; p.raise_flag = raise_flag;
     p.n_slots = d->n_samples * (long long)d->n_dims;
     p.D = d->n_dims; p.E = d->n_ctx; p.layout = d->layout; p.Q = d->nb_steps; p.out_act = d->out_act;
     p.rps = d->nb_steps + 1 + (out_fx ? 1 : 0) + (out_fx0 ? 1 : 0);
@@ -642,16 +710,18 @@ int launch_forward_tc(const umnn_desc* d, const float* x0, const float* x, const
     p.slot0 = 0;
     p.S = make_tc_smem(p.L, p.rps, p.Q);
     if (p.S.total > kTcMaxSmem) {
-        set_error("BF16X3: needs %u bytes of shared memory (max %zu)", p.S.total, kTcMaxSmem);
+        set_error("tensor-core forward: needs %u bytes of shared memory (max %zu)", p.S.total, kTcMaxSmem);
         return UMNN_ERR_UNSUPPORTED;
     }
     if (p.n_slots == 0) return 0;
+    // narrow shape: two co-resident CTAs per SM, each with half of the tensor memory
+    const bool narrow = tc_narrow_enabled() && tc_layout_is_narrow(p.L) && p.S.total <= kTcNarrowMaxSmem;
     int dev = 0, n_sm = 0;
     UMNN_CUDA_TRY(cudaGetDevice(&dev));
     UMNN_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     const long long total_rows = p.n_slots * p.rps;
     long long n_cta = (total_rows + kTcTile - 1) / kTcTile;
-    const long long cap = (long long)(n_sm / 2) * 2;
+    const long long cap = (long long)(n_sm / 2) * 2 * (narrow ? 2 : 1);
     if (n_cta > cap) n_cta = cap;
     if (n_cta > p.n_slots) n_cta = p.n_slots;
     n_cta = (n_cta + 1) / 2 * 2;             // whole CTA pairs
@@ -659,23 +729,11 @@ int launch_forward_tc(const umnn_desc* d, const float* x0, const float* x, const
     p.slots_per_cta = (p.n_slots + n_cta - 1) / n_cta;
     p.tiles_per_cta = (int)((p.slots_per_cta * p.rps + kTcTile - 1) / kTcTile);
 
-    auto kern = d->hidden_act == UMNN_ACT_LEAKY_RELU ? cc_forward_tc_kernel<UMNN_ACT_LEAKY_RELU, false>
-                                                     : cc_forward_tc_kernel<UMNN_ACT_RELU, false>;
-    UMNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.S.total));
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)n_cta);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = p.S.total;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    UMNN_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
-    return 0;
+    if (opf == UMNN_OPF_FP16)
+        return narrow ? launch_tc_kernel<false, true, UMNN_OPF_FP16>(d->hidden_act, p, (int)n_cta, s)
+                      : launch_tc_kernel<false, false, UMNN_OPF_FP16>(d->hidden_act, p, (int)n_cta, s);
+    return narrow ? launch_tc_kernel<false, true, UMNN_OPF_BF16>(d->hidden_act, p, (int)n_cta, s)
+                  : launch_tc_kernel<false, false, UMNN_OPF_BF16>(d->hidden_act, p, (int)n_cta, s);
 }
 
 // pass F of the tensor-core backward: the forward kernel over one chunk of slots with panel emission
@@ -699,23 +757,7 @@ int launch_forward_tc_emit(const umnn_desc* d, const float* x0, const float* x, 
         set_error("BF16X3 backward: needs %u bytes of shared memory (max %zu)", p.S.total, kTcMaxSmem);
         return UMNN_ERR_UNSUPPORTED;
     }
-    auto kern = d->hidden_act == UMNN_ACT_LEAKY_RELU ? cc_forward_tc_kernel<UMNN_ACT_LEAKY_RELU, true>
-                                                     : cc_forward_tc_kernel<UMNN_ACT_RELU, true>;
-    UMNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.S.total));
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)n_cta);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = p.S.total;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    UMNN_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
-    return 0;
+    return launch_tc_kernel<true, false, UMNN_OPF_BF16>(d->hidden_act, p, n_cta, s);
 }
 
 bool tc_two_segments_public() { return tc_two_segments(); }

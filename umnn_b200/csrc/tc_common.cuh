@@ -4,6 +4,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -193,6 +194,13 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// Same, with the operand formats as arguments (kind::f16 encodes A and B separately: 0 = F16, 1 = BF16).
+#define UMNN_OPF_FP16 0
+#define UMNN_OPF_BF16 1
+__host__ __device__ constexpr uint32_t make_idesc_f32(int M, int N, int a_fmt, int b_fmt) {
+    return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // ---------------------------------------------------------------------------------------------
 // MMA issue (ONE thread) and completion
 // ---------------------------------------------------------------------------------------------
@@ -248,6 +256,24 @@ __device__ __forceinline__ void split_bf16x2(float even, float odd, uint32_t& hi
     const float he = __uint_as_float(hi << 16);
     const float ho = __uint_as_float(hi & 0xFFFF0000u);
     lo = pack_bf16x2(even - he, odd - ho);
+}
+
+// fp16 hi/lo split:  v = hi + lo + O(2^-23 |v|) for 2^-3 <= |v| <= 65504 (absolute error <= 2^-25 below: lo is
+// subnormal there); |v| > 65504 overflows to inf (hi) / NaN (lo) -- the caller's overflow flag catches that.
+__device__ __forceinline__ uint32_t pack_f16x2(float even, float odd) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(odd), "f"(even));  // first source -> upper half
+    return r;
+}
+__device__ __forceinline__ void split_f16x2(float even, float odd, uint32_t& hi, uint32_t& lo) {
+    hi = pack_f16x2(even, odd);
+    const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    lo = pack_f16x2(even - h.x, odd - h.y);
+}
+template <int OPF>
+__device__ __forceinline__ void split_x2(float even, float odd, uint32_t& hi, uint32_t& lo) {
+    if constexpr (OPF == UMNN_OPF_BF16) split_bf16x2(even, odd, hi, lo);
+    else split_f16x2(even, odd, hi, lo);
 }
 
 // sign bits of 16 fp32 bit patterns, element 4k + j -> bit 8j + k (see mask_bitpos in tc_bwd_layout.cuh):

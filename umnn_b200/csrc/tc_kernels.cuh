@@ -31,6 +31,8 @@ struct TcParams {
     int tiles_per_cta;
     int D, E, layout, Q, rps, out_act;
     int x_row;             // 1: the first extra row of a slot (node Q+1) is evaluated at x, else at x0
+    const int* run_if;     // not NULL: the whole launch is a no-op unless *run_if != 0 (guarded bf16 re-run)
+    int* raise_flag;       // not NULL (fp16 operands): set when an activation overflowed the fp16 range
     TcLayout L;
     TcSmem S;
     TcEmit emit;

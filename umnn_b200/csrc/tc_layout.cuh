@@ -33,7 +33,9 @@ constexpr int kTcMaxMmaLayers = UMNN_MAX_LAYERS - 2;
 constexpr int kTcTile = 128;           // rows per CTA tile (256 per CTA pair)
 constexpr int kTcPrepBufs = 3;
 constexpr int kTcRegionCols = 256;     // TMEM columns per region (P = [0,256), Q = [256,512))
+constexpr int kTcNarrowRegionCols = 128;   // "narrow" kernel shape: two CTAs per SM, regions of 128 columns
 constexpr size_t kTcMaxSmem = 232448;  // 227 KB
+constexpr size_t kTcNarrowMaxSmem = 115712;  // (228 KB - 2 x 1 KB reserved) / 2 CTAs per SM
 
 struct TcMmaLayer {
     int h_in, h_out;      // true widths
@@ -113,6 +115,14 @@ inline bool make_tc_layout(const umnn_desc* d, TcLayout* L, bool two_segments = 
     return true;
 }
 
+// true if every padded width fits the 128-column regions of the narrow kernel shape
+inline bool tc_layout_is_narrow(const TcLayout& L) {
+    if (L.npad1 > kTcNarrowRegionCols || L.npadL > kTcNarrowRegionCols) return false;
+    for (int m = 0; m < L.n_mma; ++m)
+        if (L.layer[m].kpad > kTcNarrowRegionCols || L.layer[m].npad > kTcNarrowRegionCols) return false;
+    return true;
+}
+
 // dynamic shared memory map of the forward kernel (byte offsets from the 1024-aligned base)
 struct TcSmem {
     uint32_t off_cvec, off_hbuf, off_xnode, off_lsrel, off_node, off_part, off_fval, off_tabt, off_tabw, off_bars, off_holder;
@@ -142,10 +152,13 @@ inline TcSmem make_tc_smem(const TcLayout& L, int rps, int Q) {
     return S;
 }
 
-int launch_pack_tc(const umnn_desc* d, const float* flat, void* packed, cudaStream_t s);
+// operand format of the MMA operands (weights blob and in-TMEM activations): UMNN_OPF_BF16 / UMNN_OPF_FP16
+int launch_pack_tc(const umnn_desc* d, const float* flat, void* packed, int opf, cudaStream_t s);
+// run_if (device int, may be NULL): the launch is a no-op unless *run_if != 0.  raise_flag (device int, may be
+// NULL; fp16 operands only): set to 1 when an activation overflowed the fp16 range.
 int launch_forward_tc(const umnn_desc* d, const float* x0, const float* x, const float* h, const void* packed,
                       const float* nodes, const float* weights, float* out, float* out_fx, float* out_fx0,
-                      cudaStream_t s);
+                      int opf, const int* run_if, int* raise_flag, cudaStream_t s);
 size_t tc_packed_bytes(const umnn_desc* d);
 // 0 if the tensor-core kernel can serve desc (with `extra_rows` = 0..2 extra rows per slot), else a reason string
 const char* tc_unsupported_reason(const umnn_desc* d, int extra_rows);

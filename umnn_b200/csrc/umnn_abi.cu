@@ -2,11 +2,13 @@
 // kernels, error strings.  No torch types; plain pointers and sizes only.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
 
 #include "umnn_common.cuh"
+#include "tc_common.cuh"
 #include "tc_layout.cuh"
 #include "tc_kernels.cuh"
 
@@ -67,7 +69,8 @@ int validate_desc(const umnn_desc* d) {
     if (d->nb_steps < 1 || d->nb_steps > UMNN_MAX_STEPS) {
         set_error("desc.nb_steps=%d out of range [1, %d]", d->nb_steps, UMNN_MAX_STEPS); return UMNN_ERR_DESC;
     }
-    if (d->precision != UMNN_PREC_FP32 && d->precision != UMNN_PREC_BF16X3 && d->precision != UMNN_PREC_AUTO) {
+    if (d->precision != UMNN_PREC_FP32 && d->precision != UMNN_PREC_BF16X3 && d->precision != UMNN_PREC_AUTO &&
+        d->precision != UMNN_PREC_FP16X3) {
         set_error("desc.precision=%d is not a UMNN_PREC_*", d->precision); return UMNN_ERR_DESC;
     }
     if ((long long)d->n_samples * d->n_dims > (1LL << 40)) {
@@ -76,22 +79,43 @@ int validate_desc(const umnn_desc* d) {
     return 0;
 }
 
-// Which kernel family serves this descriptor.  UMNN_PREC_AUTO picks the BF16x3 tensor-core kernel
-// whenever the shape fits it (checked with the worst-case 2 extra rows per slot so that packing and
-// launching agree), else the FP32 kernel.  An explicit UMNN_PREC_BF16X3 on an unsupported shape fails.
+// Which kernel family serves this descriptor.  UMNN_PREC_AUTO picks a tensor-core kernel whenever the shape fits
+// it (checked with the worst-case 2 extra rows per slot so that packing and launching agree), else the FP32
+// kernel.  Which split AUTO uses on the tensor cores is a process-wide choice: UMNN_B200_AUTO_TC = fp16x3
+// (default; guarded, see umnn_cc_forward) | bf16x3.  An explicit tensor-core precision on an unsupported shape fails.
+static int auto_tc_precision() {
+    const char* e = getenv("UMNN_B200_AUTO_TC");
+    if (e && (e[0] == 'b' || e[0] == 'B')) return UMNN_PREC_BF16X3;
+    if (e && (e[0] == 'f' || e[0] == 'F')) return UMNN_PREC_FP16X3;
+    return UMNN_PREC_BF16X3;
+}
+
 static int resolve_precision(const umnn_desc* d) {
-    if (d->precision == UMNN_PREC_AUTO) return tc_unsupported_reason(d, 2) == nullptr ? UMNN_PREC_BF16X3 : UMNN_PREC_FP32;
+    if (d->precision == UMNN_PREC_AUTO) return tc_unsupported_reason(d, 2) == nullptr ? auto_tc_precision() : UMNN_PREC_FP32;
     return d->precision;
 }
+
+static bool is_tc(int prec) { return prec == UMNN_PREC_BF16X3 || prec == UMNN_PREC_FP16X3; }
 
 static int check_tc(const umnn_desc* d, const char* who) {
     const char* why = tc_unsupported_reason(d, 2);
     if (why) {
-        set_error("%s: UMNN_PREC_BF16X3 unavailable for this shape (%s)", who, why);
+        set_error("%s: tensor-core precisions unavailable for this shape (%s)", who, why);
         return UMNN_ERR_UNSUPPORTED;
     }
     return 0;
 }
+
+// Packed block of the tensor-core precisions:
+//   [ bf16 forward blobs | dgrad blobs (when the tensor-core backward serves the shape) ]   UMNN_PREC_BF16X3
+//   [ the same, rounded up to 256 bytes | fp16 forward blobs ]                               UMNN_PREC_FP16X3
+// (the backward and the guarded re-run of an FP16X3 forward use the bf16 part)
+static size_t tc_bf16_block_bytes(const umnn_desc* d) {
+    return backward_tc_unsupported_reason(d) ? tc_packed_bytes(d) : backward_tc_packed_bytes(d);
+}
+static size_t tc_fp16_offset(const umnn_desc* d) { return (tc_bf16_block_bytes(d) + 255) / 256 * 256; }
+
+constexpr size_t kForwardFlagBytes = 256;   // workspace of a guarded FP16X3 forward: one int flag
 
 }  // namespace umnn
 
@@ -139,8 +163,10 @@ size_t umnn_packed_params_bytes(const umnn_desc* d) {
         case UMNN_PREC_FP32: return sizeof(float) * (size_t)make_fp32_layout(d).total_floats;
         case UMNN_PREC_BF16X3:
             if (check_tc(d, "umnn_packed_params_bytes")) return 0;
-            // forward blobs, followed by the transposed (dgrad) blobs when the tensor-core backward serves the shape
-            return backward_tc_unsupported_reason(d) ? tc_packed_bytes(d) : backward_tc_packed_bytes(d);
+            return tc_bf16_block_bytes(d);
+        case UMNN_PREC_FP16X3:
+            if (check_tc(d, "umnn_packed_params_bytes")) return 0;
+            return tc_fp16_offset(d) + tc_packed_bytes(d);
         default: return 0;
     }
 }
@@ -149,13 +175,17 @@ int umnn_pack_params(const umnn_desc* d, const float* flat_params, void* params_
     int rc = validate_desc(d);
     if (rc) return rc;
     if (!flat_params || !params_packed) { set_error("umnn_pack_params: NULL pointer"); return UMNN_ERR_NULL; }
-    switch (resolve_precision(d)) {
+    const int prec = resolve_precision(d);
+    switch (prec) {
         case UMNN_PREC_FP32:
             return launch_pack_fp32(d, flat_params, (float*)params_packed, (cudaStream_t)stream);
         case UMNN_PREC_BF16X3:
+        case UMNN_PREC_FP16X3:
             if ((rc = check_tc(d, "umnn_pack_params")) != 0) return rc;
-            if (backward_tc_unsupported_reason(d)) return launch_pack_tc(d, flat_params, params_packed, (cudaStream_t)stream);
-            return launch_pack_backward_tc(d, flat_params, params_packed, (cudaStream_t)stream);
+            if (backward_tc_unsupported_reason(d)) rc = launch_pack_tc(d, flat_params, params_packed, UMNN_OPF_BF16, (cudaStream_t)stream);
+            else rc = launch_pack_backward_tc(d, flat_params, params_packed, (cudaStream_t)stream);
+            if (rc || prec == UMNN_PREC_BF16X3) return rc;
+            return launch_pack_tc(d, flat_params, (uint8_t*)params_packed + tc_fp16_offset(d), UMNN_OPF_FP16, (cudaStream_t)stream);
         default:
             set_error("umnn_pack_params: precision %d is not available for this shape", d->precision);
             return UMNN_ERR_UNSUPPORTED;
@@ -164,8 +194,8 @@ int umnn_pack_params(const umnn_desc* d, const float* flat_params, void* params_
 
 size_t umnn_workspace_bytes(const umnn_desc* d, int32_t for_backward) {
     if (validate_desc(d) != 0) return 0;
-    if (!for_backward) return 0;
-    if (resolve_precision(d) == UMNN_PREC_BF16X3) {
+    if (!for_backward) return resolve_precision(d) == UMNN_PREC_FP16X3 ? kForwardFlagBytes : 0;
+    if (is_tc(resolve_precision(d))) {
         const char* why = check_tc(d, "umnn_workspace_bytes") ? "forward shape unsupported" : backward_tc_unsupported_reason(d);
         if (why) {
             set_error("umnn_workspace_bytes: tensor-core backward unavailable for this shape (%s)", why);
@@ -185,7 +215,6 @@ int umnn_cc_forward(const umnn_desc* d, const float* x0, const float* x, const f
                     float* out_f_at_x0, void* workspace, size_t workspace_bytes, void* stream) {
     int rc = validate_desc(d);
     if (rc) return rc;
-    (void)workspace; (void)workspace_bytes;
     if (d->n_samples == 0) return 0;
     if (!x || !params_packed || !nodes || !weights || !out_integral || (d->n_ctx > 0 && !h)) {
         set_error("umnn_cc_forward: required pointer is NULL"); return UMNN_ERR_NULL;
@@ -197,7 +226,25 @@ int umnn_cc_forward(const umnn_desc* d, const float* x0, const float* x, const f
         case UMNN_PREC_BF16X3:
             if ((rc = check_tc(d, "umnn_cc_forward")) != 0) return rc;
             return launch_forward_tc(d, x0, x, h, params_packed, nodes, weights, out_integral, out_f_at_x,
-                                     out_f_at_x0, (cudaStream_t)stream);
+                                     out_f_at_x0, UMNN_OPF_BF16, nullptr, nullptr, (cudaStream_t)stream);
+        case UMNN_PREC_FP16X3: {
+            // fp16 hi/lo operands carry 22 bits (bf16: ~17) but overflow above 65504.  Guarded: the kernel raises a
+            // device flag when an activation overflowed (every downstream value is NaN then), and a second launch of
+            // the bf16 kernel -- a no-op while the flag is clear -- recomputes the call.  Without a workspace the
+            // fp16 launch runs unguarded (overflow surfaces as NaN).
+            if ((rc = check_tc(d, "umnn_cc_forward")) != 0) return rc;
+            const uint8_t* fp16_blobs = (const uint8_t*)params_packed + tc_fp16_offset(d);
+            int* flag = nullptr;
+            if (workspace && workspace_bytes >= sizeof(int)) {
+                flag = (int*)workspace;
+                UMNN_CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), (cudaStream_t)stream));
+            }
+            rc = launch_forward_tc(d, x0, x, h, fp16_blobs, nodes, weights, out_integral, out_f_at_x, out_f_at_x0,
+                                   UMNN_OPF_FP16, nullptr, flag, (cudaStream_t)stream);
+            if (rc || !flag) return rc;
+            return launch_forward_tc(d, x0, x, h, params_packed, nodes, weights, out_integral, out_f_at_x, out_f_at_x0,
+                                     UMNN_OPF_BF16, flag, nullptr, (cudaStream_t)stream);
+        }
         default:
             set_error("umnn_cc_forward: precision %d is not available for this shape", d->precision);
             return UMNN_ERR_UNSUPPORTED;
@@ -211,7 +258,7 @@ int umnn_cc_backward(const umnn_desc* d, const float* x0, const float* x, const 
     int rc = validate_desc(d);
     if (rc) return rc;
     const int prec = resolve_precision(d);
-    if (prec == UMNN_PREC_BF16X3) {
+    if (is_tc(prec)) {
         if ((rc = check_tc(d, "umnn_cc_backward")) != 0) return rc;
         if (backward_tc_unsupported_reason(d)) {
             set_error("umnn_cc_backward: tensor-core backward unavailable for this shape (%s); use UMNN_PREC_FP32",
@@ -226,7 +273,7 @@ int umnn_cc_backward(const umnn_desc* d, const float* x0, const float* x, const 
     if (!x || !params_packed || !nodes || !weights || !grad_out || (d->n_ctx > 0 && !h)) {
         set_error("umnn_cc_backward: required pointer is NULL"); return UMNN_ERR_NULL;
     }
-    if (prec == UMNN_PREC_BF16X3)
+    if (is_tc(prec))
         return launch_backward_tc(d, x0, x, h, params_packed, nodes, weights, grad_out, grad_f_at_x, d_x0, d_x, d_h, d_params,
                                   workspace, workspace_bytes, (cudaStream_t)stream);
     return launch_backward_fp32(d, x0, x, h, (const float*)params_packed, nodes, weights, grad_out, grad_f_at_x, d_x0, d_x,
@@ -248,6 +295,7 @@ int umnn_cc_forward_host(const umnn_desc* d, const float* x0_host, const float* 
     const size_t hb = (size_t)d->n_samples * d->n_dims * d->n_ctx * sizeof(float);
     const size_t pb = (size_t)umnn_param_count(d) * sizeof(float);
     const size_t packed_b = umnn_packed_params_bytes(d);
+    const size_t ws_b = umnn_workspace_bytes(d, 0);
     const int Q = d->nb_steps;
     std::vector<float> tabs(2 * (Q + 1));
     rc = umnn_cc_tables(Q, tabs.data(), tabs.data() + Q + 1);
@@ -257,7 +305,7 @@ int umnn_cc_forward_host(const umnn_desc* d, const float* x0_host, const float* 
     auto al = [](size_t v) { return (v + 255) / 256 * 256; };
     const size_t o_x0 = 0, o_x = o_x0 + al(xb), o_h = o_x + al(xb), o_p = o_h + al(hb), o_pk = o_p + al(pb),
                  o_t = o_pk + al(packed_b), o_out = o_t + al(tabs.size() * sizeof(float)), o_fx = o_out + al(xb),
-                 o_fx0 = o_fx + al(xb), total = o_fx0 + al(xb);
+                 o_fx0 = o_fx + al(xb), o_ws = o_fx0 + al(xb), total = o_ws + al(ws_b);
     char* slab = nullptr;
     UMNN_CUDA_TRY(cudaMalloc((void**)&slab, total));
     cudaStream_t s = 0;
@@ -278,7 +326,7 @@ int umnn_cc_forward_host(const umnn_desc* d, const float* x0_host, const float* 
                          (const float*)(slab + o_h), slab + o_pk, (const float*)(slab + o_t),
                          (const float*)(slab + o_t) + Q + 1, (float*)(slab + o_out),
                          out_f_at_x_host ? (float*)(slab + o_fx) : nullptr,
-                         out_f_at_x0_host ? (float*)(slab + o_fx0) : nullptr, nullptr, 0, s);
+                         out_f_at_x0_host ? (float*)(slab + o_fx0) : nullptr, ws_b ? slab + o_ws : nullptr, ws_b, s);
     if (rc) return fail(rc);
     UMNN_HOST_TRY(cudaMemcpyAsync(out_integral_host, slab + o_out, xb, cudaMemcpyDeviceToHost, s));
     if (out_f_at_x_host) UMNN_HOST_TRY(cudaMemcpyAsync(out_f_at_x_host, slab + o_fx, xb, cudaMemcpyDeviceToHost, s));

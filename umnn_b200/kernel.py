@@ -14,11 +14,12 @@ from . import _native
 from .networks import KernelSpec
 from .quadrature import device_tables
 
-_PRECISION_ENV = {"fp32": _native.PREC_FP32, "bf16x3": _native.PREC_BF16X3, "auto": _native.PREC_AUTO}
+_PRECISION_ENV = {"fp32": _native.PREC_FP32, "bf16x3": _native.PREC_BF16X3, "fp16x3": _native.PREC_FP16X3,
+                  "auto": _native.PREC_AUTO}
 
 
 def default_precision() -> int:
-    """UMNN_B200_PRECISION = fp32 | bf16x3 | auto (default auto)."""
+    """UMNN_B200_PRECISION = fp32 | bf16x3 | fp16x3 | auto (default auto)."""
     return _PRECISION_ENV[os.environ.get("UMNN_B200_PRECISION", "auto").lower()]
 
 
