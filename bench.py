@@ -172,7 +172,7 @@ def run_reference(args, cfg, name):
     print(json.dumps(out), flush=True)
 
 
-AUTO_TC_DEFAULT = "bf16x3"   # what UMNN_PREC_AUTO resolves to on the tensor cores (umnn_abi.cu: auto_tc_precision)
+AUTO_TC_DEFAULT = "fp16x3"   # what UMNN_PREC_AUTO resolves to on the tensor cores (umnn_abi.cu: auto_tc_precision)
 
 
 def torch_route_probe(net, cfg, dev, Bs=256, reps=3):

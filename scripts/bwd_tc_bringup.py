@@ -10,15 +10,17 @@ CASES = {
     "cfg5": (100, 784, 30, [100, 50, 50, 50, 50], 50, True),
     "odd": (37, 3, 1, [20, 20], 40, True),
     "cfg4s": (1024, 63, 30, [200, 200, 200], 100, True),
+    "cfg3_trained": (10000, 6, 30, [200, 200, 200], 50, True, 2.5),
 }
 
 def run_case(name):
     import numpy as np, torch
     from oracle import umnn_oracle as orc
     from umnn_b200 import IntegrandNetwork, kernel, _native
-    B, D, E, hidden, Q, jac = CASES[name]
+    B, D, E, hidden, Q, jac = CASES[name][:6]
+    gain = CASES[name][6] if len(CASES[name]) > 6 else 1.0
     spec = orc.MLPSpec(tuple([1 + E] + hidden + [1]))
-    flat = orc.synth_params(spec, 0)
+    flat = orc.synth_params(spec, 0, gain)
     x0, x, h, g = orc.synth_inputs(B, D, E * D, 1, x0_zero=False)
     gfx = np.random.RandomState(3).standard_normal(x.shape).astype(np.float32) if jac else None
     net = IntegrandNetwork(D, 1 + E, hidden, 1)
@@ -31,7 +33,7 @@ def run_case(name):
     tg = None if gfx is None else torch.from_numpy(gfx).to(dev)
     ks = net.kernel_spec()
     res = {}
-    for pname, prec in (("fp32", _native.PREC_FP32), ("bf16x3", _native.PREC_BF16X3)):
+    for pname, prec in (("fp32", _native.PREC_FP32), ("bf16x3", _native.PREC_BF16X3), ("fp16x3", _native.PREC_FP16X3)):
         fn = lambda: kernel.cc_backward(ks, t[0], t[1], t[2], t[3], Q, grad_fx=tg, precision=prec)
         out = fn(); torch.cuda.synchronize()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -40,10 +42,15 @@ def run_case(name):
         e.record(); torch.cuda.synchronize()
         res[pname] = (s.elapsed_time(e) / 3, [o.cpu().numpy() for o in out])
     def rtm(a, b): return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
-    a, b = res["bf16x3"][1], res["fp32"][1]
-    print(f"{name}: fp32 {res['fp32'][0]:.2f} ms, bf16x3 {res['bf16x3'][0]:.2f} ms ({res['fp32'][0] / res['bf16x3'][0]:.1f}x)  "
-          f"rel-to-max vs fp32: dx0={rtm(a[0], b[0]):.2e} dx={rtm(a[1], b[1]):.2e} dflat={rtm(a[2], b[2]):.2e} dh={rtm(a[3], b[3]):.2e}",
-          flush=True)
+    def nrm(a, b): return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-30))
+    b = res["fp32"][1]
+    line = f"{name}: fp32 {res['fp32'][0]:.2f} ms"
+    for pname in ("bf16x3", "fp16x3"):
+        a = res[pname][1]
+        line += (f" | {pname} {res[pname][0]:.2f} ms ({res['fp32'][0] / res[pname][0]:.1f}x) rel-to-max vs fp32: dx0={rtm(a[0], b[0]):.2e} "
+                 f"dx={rtm(a[1], b[1]):.2e} dflat={rtm(a[2], b[2]):.2e} dh={rtm(a[3], b[3]):.2e} normwise dflat={nrm(a[2], b[2]):.2e} "
+                 f"dh={nrm(a[3], b[3]):.2e}")
+    print(line, flush=True)
 
 if __name__ == "__main__":
     if len(sys.argv) > 1:

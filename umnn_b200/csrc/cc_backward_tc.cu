@@ -56,6 +56,7 @@ struct TcDgradParams {
     float *d_x0, *d_x, *d_h;
     long long slot0, n_slots, slots_per_cta, row_block;
     int tiles_per_cta, D, E, layout, Q, rps, out_act;
+    const int* run_if;                         // not NULL: no-op unless *run_if != 0 (guarded bf16 re-run)
     TcDgradLayout L;
     TcDgradSmem S;
 };
@@ -85,6 +86,7 @@ __device__ __forceinline__ float times_slope(float v, uint32_t bits, int c) {
 
 template <int HIDDEN_ACT>
 __global__ void __launch_bounds__(kThreads, 1) cc_dgrad_tc_kernel(const __grid_constant__ TcDgradParams p) {
+    if (p.run_if != nullptr && *p.run_if == 0) return;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -468,10 +470,13 @@ struct TcWgradParams {
     long long n_blocks;          // 16-row blocks in the chunk
     TcWgradPlan W;
     int n_stages;                // ring depth (2..kWMaxStages), as many as fit in shared memory
+    int act_fmt;                 // operand format of the activation panels A_1..A_J (UMNN_OPF_*); A_0 and DZ_* are bf16
+    const int* run_if;           // not NULL: no-op unless *run_if != 0
     int src_w_off[UMNN_MAX_LAYERS], src_b_off[UMNN_MAX_LAYERS];
 };
 
 __global__ void __launch_bounds__(kWThreads, 1) cc_wgrad_tc_kernel(const __grid_constant__ TcWgradParams p) {
+    if (p.run_if != nullptr && *p.run_if == 0) return;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) uint64_t full[kWMaxStages], empty[kWMaxStages], done, peer_ready[kWMaxStages];
@@ -558,7 +563,12 @@ __global__ void __launch_bounds__(kWThreads, 1) cc_wgrad_tc_kernel(const __grid_
                 const uint32_t stage_addr = sbase + (uint32_t)st * W.stage_bytes;
                 for (int l = 0; l < W.n_layers; ++l) {
                     const TcWgradLayer& y = W.layer[l];
-                    const uint32_t idesc = make_idesc_bf16_f32(256, y.n_width) | (1u << 15) | (1u << 16);
+                    // kind::f16 takes the A and B formats separately: activation panels A_1..A_J may be fp16 while
+                    // A_0 and the dz panels are bf16 (panel table: A_0..A_J, then DZ_1..DZ_{J+1})
+                    const int J = W.n_layers - 1;
+                    const int m_fmt = (y.m_panel >= 1 && y.m_panel <= J) ? p.act_fmt : UMNN_OPF_BF16;
+                    const int n_fmt = (y.n_panel >= 1 && y.n_panel <= J) ? p.act_fmt : UMNN_OPF_BF16;
+                    const uint32_t idesc = make_idesc_f32(256, y.n_width, m_fmt, n_fmt) | (1u << 15) | (1u << 16);
                     // tiles hold [hi | lo] x [k8][W/16 core matrices]; the M tile is read 128 rows deep although only
                     // W/2 are staged (rows beyond feed accumulator rows nobody reads)
                     const uint32_t lbo_m = (uint32_t)(y.m_width / 16) * 128u, lbo_n = (uint32_t)(y.n_width / 16) * 128u;
@@ -625,7 +635,8 @@ __global__ void __launch_bounds__(kWThreads, 1) cc_wgrad_tc_kernel(const __grid_
 }
 
 __global__ void reduce_partials_tc_kernel(const float* __restrict__ part, long long P, int n_part, float* __restrict__ d_params,
-                                          int accumulate) {
+                                          int accumulate, const int* __restrict__ run_if) {
+    if (run_if != nullptr && *run_if == 0) return;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     float s = accumulate ? d_params[i] : 0.0f;
@@ -645,7 +656,7 @@ struct BwdTcPlan {
     int rps, n_cta, tiles, n_pairs_w;
     long long slots_per_cta, chunk_slots, row_block, R_pad;
     size_t panel_bytes[2 * UMNN_MAX_LAYERS + 2];
-    size_t off_panel[2 * UMNN_MAX_LAYERS + 2], off_mask[UMNN_MAX_LAYERS], off_v, off_part, total_bytes;
+    size_t off_panel[2 * UMNN_MAX_LAYERS + 2], off_mask[UMNN_MAX_LAYERS], off_v, off_part, off_flag, total_bytes;
     size_t w_smem;
     int w_stages;
 };
@@ -707,6 +718,7 @@ const char* make_bwd_plan(const umnn_desc* d, BwdTcPlan* B) {
     for (int j = 1; j <= B->G.J; ++j) B->off_mask[j] = take((size_t)B->R_pad * 8 * 4);
     B->off_v = take((size_t)B->R_pad * 4);
     B->off_part = take((size_t)B->n_pairs_w * B->P * 4);
+    B->off_flag = take(sizeof(int));
     B->total_bytes = off + 256;
     return nullptr;
 }
@@ -748,7 +760,7 @@ int launch_pack_backward_tc(const umnn_desc* d, const float* flat, void* packed,
 int launch_backward_tc(const umnn_desc* d, const float* x0, const float* x, const float* h, const void* packed,
                        const float* nodes, const float* weights, const float* grad_out, const float* grad_fx,
                        float* d_x0, float* d_x, float* d_h, float* d_params, void* workspace, size_t workspace_bytes,
-                       cudaStream_t s) {
+                       const void* fwd_blobs_fp16, cudaStream_t s) {
     BwdTcPlan B;
     const char* why = make_bwd_plan(d, &B);
     if (why) { set_error("BF16X3 backward: %s", why); return UMNN_ERR_UNSUPPORTED; }
@@ -802,39 +814,57 @@ int launch_backward_tc(const umnn_desc* d, const float* x0, const float* x, cons
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
 
-    bool first = true;
-    for (long long s0 = 0; s0 < n_slots; s0 += B.chunk_slots) {
-        const long long cs = (n_slots - s0 < B.chunk_slots) ? (n_slots - s0) : B.chunk_slots;
-        // pass F
-        int rc = launch_forward_tc_emit(d, x0, x, h, fwd_blobs, nodes, weights, s0, cs, B.slots_per_cta, B.tiles, B.n_cta, emit, s);
-        if (rc) return rc;
-        // pass D
-        g.slot0 = s0;
-        g.n_slots = cs;
-        {
-            cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3((unsigned)B.n_cta);
-            cfg.blockDim = dim3(kThreads);
-            cfg.dynamicSmemBytes = B.GS.total;
-            cfg.stream = s;
-            cfg.attrs = attr;
-            cfg.numAttrs = 1;
-            UMNN_CUDA_TRY(cudaLaunchKernelEx(&cfg, dkern, g));
+    // fwd_blobs_fp16 != NULL: pass F re-evaluates the network with fp16 hi/lo operands (22 bits: far fewer
+    // LeakyReLU units flip side against the fp32 forward than with bf16's ~17) and writes A_1..A_J as fp16 panels,
+    // which pass W multiplies with the bf16 dz panels directly.  An activation beyond the fp16 range raises the
+    // flag; the whole backward is then repeated with bf16 operands by a second sequence of launches that are
+    // no-ops while the flag is clear.
+    int* flag = reinterpret_cast<int*>(ws + B.off_flag);
+    const int n_attempts = fwd_blobs_fp16 ? 2 : 1;
+    if (fwd_blobs_fp16) UMNN_CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), s));
+    for (int attempt = 0; attempt < n_attempts; ++attempt) {
+        const bool fp16_act = fwd_blobs_fp16 && attempt == 0;
+        const int* run_if = (fwd_blobs_fp16 && attempt == 1) ? flag : nullptr;
+        g.run_if = run_if;
+        w.run_if = run_if;
+        w.act_fmt = fp16_act ? UMNN_OPF_FP16 : UMNN_OPF_BF16;
+        bool first = true;
+        for (long long s0 = 0; s0 < n_slots; s0 += B.chunk_slots) {
+            const long long cs = (n_slots - s0 < B.chunk_slots) ? (n_slots - s0) : B.chunk_slots;
+            // pass F
+            int rc = launch_forward_tc_emit(d, x0, x, h, fp16_act ? (const uint8_t*)fwd_blobs_fp16 : fwd_blobs, nodes, weights, s0, cs,
+                                            B.slots_per_cta, B.tiles, B.n_cta, emit, fp16_act ? UMNN_OPF_FP16 : UMNN_OPF_BF16,
+                                            run_if, fp16_act ? flag : nullptr, s);
+            if (rc) return rc;
+            // pass D
+            g.slot0 = s0;
+            g.n_slots = cs;
+            {
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = dim3((unsigned)B.n_cta);
+                cfg.blockDim = dim3(kThreads);
+                cfg.dynamicSmemBytes = B.GS.total;
+                cfg.stream = s;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                UMNN_CUDA_TRY(cudaLaunchKernelEx(&cfg, dkern, g));
+            }
+            // pass W
+            if (d_params) {
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = dim3((unsigned)(2 * B.n_pairs_w));
+                cfg.blockDim = dim3(kWThreads);
+                cfg.dynamicSmemBytes = B.w_smem;
+                cfg.stream = s;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                UMNN_CUDA_TRY(cudaLaunchKernelEx(&cfg, cc_wgrad_tc_kernel, w));
+                reduce_partials_tc_kernel<<<(unsigned)((B.P + 255) / 256), 256, 0, s>>>(w.part, B.P, B.n_pairs_w, d_params,
+                                                                                       first ? 0 : 1, run_if);
+                UMNN_CUDA_TRY(cudaGetLastError());
+            }
+            first = false;
         }
-        // pass W
-        if (d_params) {
-            cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3((unsigned)(2 * B.n_pairs_w));
-            cfg.blockDim = dim3(kWThreads);
-            cfg.dynamicSmemBytes = B.w_smem;
-            cfg.stream = s;
-            cfg.attrs = attr;
-            cfg.numAttrs = 1;
-            UMNN_CUDA_TRY(cudaLaunchKernelEx(&cfg, cc_wgrad_tc_kernel, w));
-            reduce_partials_tc_kernel<<<(unsigned)((B.P + 255) / 256), 256, 0, s>>>(w.part, B.P, B.n_pairs_w, d_params, first ? 0 : 1);
-            UMNN_CUDA_TRY(cudaGetLastError());
-        }
-        first = false;
     }
     return 0;
 }

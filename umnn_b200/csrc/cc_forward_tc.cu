@@ -108,7 +108,7 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
     constexpr int kEpiWarps = C::kEpiWarps, kColGroups = C::kColGroups, kPrepWarps = C::kPrepWarps;
     constexpr int kMmaWarp = C::kMmaWarp, kThreads = C::kThreads, kEpiThreads = C::kEpiThreads, kPrepThreads = C::kPrepThreads;
     constexpr uint32_t kColP = C::kColP, kColQ = C::kColQ;
-    static_assert(!(EMIT && (NARROW || OPF != UMNN_OPF_BF16)), "pass F runs the wide bf16 shape");
+    static_assert(!(EMIT && NARROW), "pass F runs the wide shape");
     // guarded re-run (see launch_forward_tc): nothing to do unless the first attempt raised the flag
     if (p.run_if != nullptr && *p.run_if == 0) return;
     extern __shared__ uint8_t smem_raw[];
@@ -282,7 +282,8 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
             }
             prep_bar_sync<kPrepThreads>();
             if (EMIT) {
-                // A_0 = [x_row, h_slot, 1, 0...] as bf16 hi / lo (operand of the first layer's weight gradient)
+                // A_0 = [x_row, h_slot, 1, 0...] as bf16 hi / lo (operand of the first layer's weight gradient); the raw
+                // inputs stay bf16 in every mode: their range is the caller's, not the network's
                 const int W0 = p.emit.width[0];
                 const int n_gran = W0 / 8;
                 for (int idx = ptid; idx < kTcTile * n_gran; idx += kPrepThreads) {
@@ -335,6 +336,7 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
         const uint32_t col_last = ((n_mma - 1) & 1) ? kColQ : kColP;   // accumulator region of the last MMA layer
         const TcMmaLayer& ylast = L.layer[n_mma - 1];
         float carry = 0.0f;
+        float amax = 0.0f;     // largest |activation| this thread turned into an fp16 operand
 
         mbar_wait(&bars[BAR_WLOAD], 0, 130);
 
@@ -349,7 +351,7 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float v0 = fmaf(xn, wx[2 * i], cv[2 * i]), v1 = fmaf(xn, wx[2 * i + 1], cv[2 * i + 1]);
-                split_x2<OPF>(hact<HIDDEN_ACT>(v0), hact<HIDDEN_ACT>(v1), o[i], o[8 + i]);
+                split_track<OPF>(hact<HIDDEN_ACT>(v0), hact<HIDDEN_ACT>(v1), o[i], o[8 + i], amax);
                 if (EMIT) { pre[2 * i] = __float_as_uint(v0); pre[2 * i + 1] = __float_as_uint(v1); }
             }
             tmem_st16(tbase + lane_sel + kColQ + 16u * c16, o);
@@ -403,15 +405,15 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
                     if (EMIT) prow = panel_row(p.emit.a[m + 2], pr, y.npad);
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
-                        split_x2<OPF>(hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i + 1])),
-                                     o[i], o[8 + i]);
+                        split_track<OPF>(hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i + 1])),
+                                     o[i], o[8 + i], amax);
                     tmem_st16(taddr, o);
                     if (EMIT) emit16(prow, 32 * pp, o);
                     if (two) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
-                            split_x2<OPF>(hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i + 1])),
-                                         o[i], o[8 + i]);
+                            split_track<OPF>(hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i + 1])),
+                                         o[i], o[8 + i], amax);
                         tmem_st16(taddr + 16, o);
                         if (EMIT) emit16(prow, 32 * pp + 16, o);
                     }
@@ -450,14 +452,14 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
                         uint32_t o[16];
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
-                            split_x2<OPF>(hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i + 1])),
-                                         o[i], o[8 + i]);
+                            split_track<OPF>(hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i + 1])),
+                                         o[i], o[8 + i], amax);
                         emit16(prow, 32 * pp, o);
                         if (two) {
 #pragma unroll
                             for (int i = 0; i < 8; ++i)
-                                split_x2<OPF>(hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i + 1])),
-                                             o[i], o[8 + i]);
+                                split_track<OPF>(hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i + 1])),
+                                             o[i], o[8 + i], amax);
                             emit16(prow, 32 * pp + 16, o);
                         }
                         p.emit.mask[n_mma + 1][pr * 8 + pp] = sign_mask16(v0) | (two ? sign_mask16(v1) << 4 : 0u);
@@ -489,9 +491,6 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
                 for (int g = 1; g < kColGroups; ++g) vtot += part[(g - 1) * kTcTile + r];
                 if (EMIT) p.emit.v[cta_row0 + row0 + r] = node >= 0 ? vtot : 0.0f;
                 if (node >= 0) {
-                    // an fp16 operand that overflowed (|activation| > 65504) has turned every downstream unit
-                    // into NaN: ask for the bf16 re-run
-                    if (OPF == UMNN_OPF_FP16 && p.raise_flag != nullptr && !(fabsf(vtot) <= 3.0e38f)) *p.raise_flag = 1;
                     const float f = out_act(vtot, p.out_act);
                     if (node <= p.Q) {
                         fval[r] = f * tab_w[node];
@@ -533,6 +532,8 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[BAR_PREP_EMPTY + b]);
         }
+        // an activation beyond the fp16 range became inf in its operand: ask for the bf16 re-run
+        if (OPF == UMNN_OPF_FP16 && p.raise_flag != nullptr && amax > kFp16Max) *p.raise_flag = 1;
     }
 
     // ---------------------------------------------------------------- teardown
@@ -739,7 +740,8 @@ int launch_forward_tc(const umnn_desc* d, const float* x0, const float* x, const
 // pass F of the tensor-core backward: the forward kernel over one chunk of slots with panel emission
 int launch_forward_tc_emit(const umnn_desc* d, const float* x0, const float* x, const float* h, const void* packed,
                            const float* nodes, const float* weights, long long slot0, long long n_slots_chunk,
-                           long long slots_per_cta, int tiles_per_cta, int n_cta, const TcEmit& emit, cudaStream_t s) {
+                           long long slots_per_cta, int tiles_per_cta, int n_cta, const TcEmit& emit, int opf,
+                           const int* run_if, int* raise_flag, cudaStream_t s) {
     TcParams p{};
     if (!make_tc_layout(d, &p.L, tc_two_segments())) {
         set_error("BF16X3: shape not supported by the tensor-core kernel");
@@ -747,6 +749,7 @@ int launch_forward_tc_emit(const umnn_desc* d, const float* x0, const float* x, 
     }
     p.x0 = x0; p.x = x; p.h = h; p.nodes = nodes; p.weights = weights; p.blobs = (const uint8_t*)packed;
     p.out = nullptr; p.out_fx = nullptr; p.out_fx0 = nullptr;
+    p.run_if = run_if; p.raise_flag = raise_flag;
     p.slot0 = slot0; p.n_slots = n_slots_chunk; p.slots_per_cta = slots_per_cta; p.tiles_per_cta = tiles_per_cta;
     p.D = d->n_dims; p.E = d->n_ctx; p.layout = d->layout; p.Q = d->nb_steps; p.out_act = d->out_act;
     p.rps = d->nb_steps + 3;
@@ -757,7 +760,8 @@ int launch_forward_tc_emit(const umnn_desc* d, const float* x0, const float* x, 
         set_error("BF16X3 backward: needs %u bytes of shared memory (max %zu)", p.S.total, kTcMaxSmem);
         return UMNN_ERR_UNSUPPORTED;
     }
-    return launch_tc_kernel<true, false, UMNN_OPF_BF16>(d->hidden_act, p, n_cta, s);
+    return opf == UMNN_OPF_FP16 ? launch_tc_kernel<true, false, UMNN_OPF_FP16>(d->hidden_act, p, n_cta, s)
+                                : launch_tc_kernel<true, false, UMNN_OPF_BF16>(d->hidden_act, p, n_cta, s);
 }
 
 bool tc_two_segments_public() { return tc_two_segments(); }

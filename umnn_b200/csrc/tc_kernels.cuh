@@ -8,7 +8,8 @@ namespace umnn {
 
 // panels written by pass F (EMIT) for one chunk of rows; index j = hidden layer (0 = network input)
 struct TcEmit {
-    uint8_t* a[UMNN_MAX_LAYERS];       // A_j panels (bf16 hi and lo interleaved per block, see tc_bwd_layout.cuh)
+    uint8_t* a[UMNN_MAX_LAYERS];       // A_j panels (16-bit hi and lo interleaved per block, see tc_bwd_layout.cuh); A_0 is
+                                       // always bf16, A_1..A_J carry the operand format of the launch (bf16 or fp16)
     uint32_t* mask[UMNN_MAX_LAYERS];   // [R_pad][8] sign bits per 32-column pair, j = 1..J
     float* v;                          // [R_pad] pre-output-activation
     int width[UMNN_MAX_LAYERS];        // panel widths P_j
@@ -40,17 +41,18 @@ struct TcParams {
 
 int launch_forward_tc_emit(const umnn_desc* d, const float* x0, const float* x, const float* h, const void* packed,
                            const float* nodes, const float* weights, long long slot0, long long n_slots_chunk,
-                           long long slots_per_cta, int tiles_per_cta, int n_cta, const TcEmit& emit, cudaStream_t s);
+                           long long slots_per_cta, int tiles_per_cta, int n_cta, const TcEmit& emit, int opf,
+                           const int* run_if, int* raise_flag, cudaStream_t s);
 bool tc_two_segments_public();
 
 // tensor-core backward (cc_backward_tc.cu)
 const char* backward_tc_unsupported_reason(const umnn_desc* d);
 size_t backward_tc_workspace_bytes(const umnn_desc* d);
-size_t backward_tc_packed_bytes(const umnn_desc* d);      // forward blobs + dgrad blobs
+size_t backward_tc_packed_bytes(const umnn_desc* d);      // bf16 forward blobs + dgrad blobs
 int launch_pack_backward_tc(const umnn_desc* d, const float* flat, void* packed, cudaStream_t s);
 int launch_backward_tc(const umnn_desc* d, const float* x0, const float* x, const float* h, const void* packed,
                        const float* nodes, const float* weights, const float* grad_out, const float* grad_fx,
                        float* d_x0, float* d_x, float* d_h, float* d_params, void* workspace, size_t workspace_bytes,
-                       cudaStream_t s);
+                       const void* fwd_blobs_fp16, cudaStream_t s);
 
 }  // namespace umnn

@@ -86,8 +86,7 @@ int validate_desc(const umnn_desc* d) {
 static int auto_tc_precision() {
     const char* e = getenv("UMNN_B200_AUTO_TC");
     if (e && (e[0] == 'b' || e[0] == 'B')) return UMNN_PREC_BF16X3;
-    if (e && (e[0] == 'f' || e[0] == 'F')) return UMNN_PREC_FP16X3;
-    return UMNN_PREC_BF16X3;
+    return UMNN_PREC_FP16X3;
 }
 
 static int resolve_precision(const umnn_desc* d) {
@@ -275,7 +274,9 @@ int umnn_cc_backward(const umnn_desc* d, const float* x0, const float* x, const 
     }
     if (is_tc(prec))
         return launch_backward_tc(d, x0, x, h, params_packed, nodes, weights, grad_out, grad_f_at_x, d_x0, d_x, d_h, d_params,
-                                  workspace, workspace_bytes, (cudaStream_t)stream);
+                                  workspace, workspace_bytes,
+                                  prec == UMNN_PREC_FP16X3 ? (const uint8_t*)params_packed + tc_fp16_offset(d) : nullptr,
+                                  (cudaStream_t)stream);
     return launch_backward_fp32(d, x0, x, h, (const float*)params_packed, nodes, weights, grad_out, grad_f_at_x, d_x0, d_x,
                                 d_h, d_params, workspace, workspace_bytes, (cudaStream_t)stream);
 }

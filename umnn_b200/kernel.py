@@ -62,7 +62,7 @@ def packed_parameters(spec: KernelSpec, desc: _native.Desc, device: torch.device
     owner = spec.linears[0]
     stamp = None
     if not owner.training and not _repack_always:
-        stamp = (desc.precision, str(device)) + tuple((id(p), p.data_ptr(), p._version) for p in spec.parameters())
+        stamp = (desc.precision, os.environ.get("UMNN_B200_AUTO_TC", ""), str(device)) + tuple((id(p), p.data_ptr(), p._version) for p in spec.parameters())
         hit = owner.__dict__.get("_umnn_packed", {}).get(desc.precision)
         if hit is not None and hit[0] == stamp:
             return hit[1]
@@ -155,20 +155,23 @@ def cc_forward_host(spec_widths, layout, hidden_act, out_act, flat_params, x0, x
 
 
 def backward_precision(spec: KernelSpec, x: torch.Tensor, nb_steps: int) -> Optional[int]:
-    """Which native backward serves this shape: PREC_BF16X3 (three tensor-core passes), PREC_FP32 (fused FFMA
-    kernel) or None (neither fits: the caller uses torch ops on the device).
+    """Which native backward serves this shape: a tensor-core precision (three tensor-core passes; PREC_AUTO lets the
+    library pick its default operand split, fp16x3 with a guarded bf16 re-run), PREC_FP32 (fused FFMA kernel) or None
+    (neither fits: the caller uses torch ops on the device).
 
-    UMNN_B200_BACKWARD = auto (default: tensor cores, else FFMA) | bf16x3 | fp32 | torch.
+    UMNN_B200_BACKWARD = auto (default: tensor cores, else FFMA) | fp16x3 | bf16x3 | fp32 | torch.
     """
     mode = os.environ.get("UMNN_B200_BACKWARD", "auto").lower()
     if mode == "torch":
         return None
     if mode == "bf16x3":
         cands = [_native.PREC_BF16X3]
+    elif mode == "fp16x3":
+        cands = [_native.PREC_FP16X3]
     elif mode == "fp32" or default_precision() == _native.PREC_FP32:
         cands = [_native.PREC_FP32]
     else:
-        cands = [_native.PREC_BF16X3, _native.PREC_FP32]
+        cands = [default_precision(), _native.PREC_FP32]
     if x.shape[0] == 0:
         return cands[-1]
     L = _native.lib()
