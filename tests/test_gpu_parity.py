@@ -102,6 +102,20 @@ def test_native_library_is_the_loaded_path():
     assert "libumnn_b200.so" in loaded
 
 
+@pytest.mark.parametrize("hidden,narrow,ctas", [([100, 100, 100, 100], 1, 2), ([100, 50, 50, 50, 50], 1, 2),
+                                                 ([126, 126], 1, 2), ([127, 127], 0, 1), ([200, 200, 200], 0, 1)])
+def test_narrow_shape_runs_two_ctas_per_sm(hidden, narrow, ctas):
+    """Integrands whose padded widths fit 128 tensor-memory columns get the narrow kernel shape, and the hardware
+    really holds two of its CTAs per SM (registers, shared memory and threads all allow it)."""
+    import ctypes
+    from umnn_b200 import _native
+    desc = _native.make_desc(_native.LAYOUT_STRIDED_D, 1000, 6, 30, [31] + hidden + [1], _native.ACT_LEAKY_RELU,
+                             _native.OUT_ELU_PLUS_1, 50, _native.PREC_AUTO)
+    is_narrow, n = ctypes.c_int32(-1), ctypes.c_int32(-1)
+    _native.check(_native.lib().umnn_tc_forward_occupancy(desc, 1, ctypes.byref(is_narrow), ctypes.byref(n)))
+    assert (is_narrow.value, n.value) == (narrow, ctas)
+
+
 @pytest.mark.parametrize("precision", PRECISIONS)
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_forward_matches_golden_and_oracle(name, precision):

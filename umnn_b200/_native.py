@@ -24,7 +24,7 @@ PREC_FP32, PREC_BF16X3, PREC_AUTO, PREC_FP16X3 = 0, 1, 2, 3
 
 EXPORTS = ("umnn_abi_version", "umnn_last_error", "umnn_cc_tables", "umnn_param_count",
            "umnn_packed_params_bytes", "umnn_pack_params", "umnn_workspace_bytes", "umnn_cc_forward",
-           "umnn_cc_backward", "umnn_cc_forward_host", "umnn_invert_bracket_step")
+           "umnn_cc_backward", "umnn_cc_forward_host", "umnn_invert_bracket_step", "umnn_tc_forward_occupancy")
 
 
 class Desc(ctypes.Structure):
@@ -80,6 +80,9 @@ def lib() -> ctypes.CDLL:
         L.umnn_cc_backward.argtypes = [dp, fp, fp, fp, vp, fp, fp, fp, fp, fp, fp, fp, fp, vp, ctypes.c_size_t, vp]
         L.umnn_cc_forward_host.restype = ctypes.c_int
         L.umnn_cc_forward_host.argtypes = [dp, fp, fp, fp, fp, fp, fp, fp, ctypes.c_int32]
+        L.umnn_tc_forward_occupancy.restype = ctypes.c_int
+        L.umnn_tc_forward_occupancy.argtypes = [dp, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32),
+                                                ctypes.POINTER(ctypes.c_int32)]
         i64 = ctypes.c_int64
         L.umnn_invert_bracket_step.restype = ctypes.c_int
         L.umnn_invert_bracket_step.argtypes = [i64, ctypes.c_int32, fp, fp, fp, fp, i64, fp, fp, i64, fp, fp, i64, fp, fp,

@@ -470,7 +470,6 @@ struct TcWgradParams {
     long long n_blocks;          // 16-row blocks in the chunk
     TcWgradPlan W;
     int n_stages;                // ring depth (2..kWMaxStages), as many as fit in shared memory
-    int act_fmt;                 // operand format of the activation panels A_1..A_J (UMNN_OPF_*); A_0 and DZ_* are bf16
     const int* run_if;           // not NULL: no-op unless *run_if != 0
     int src_w_off[UMNN_MAX_LAYERS], src_b_off[UMNN_MAX_LAYERS];
 };
@@ -563,12 +562,7 @@ __global__ void __launch_bounds__(kWThreads, 1) cc_wgrad_tc_kernel(const __grid_
                 const uint32_t stage_addr = sbase + (uint32_t)st * W.stage_bytes;
                 for (int l = 0; l < W.n_layers; ++l) {
                     const TcWgradLayer& y = W.layer[l];
-                    // kind::f16 takes the A and B formats separately: activation panels A_1..A_J may be fp16 while
-                    // A_0 and the dz panels are bf16 (panel table: A_0..A_J, then DZ_1..DZ_{J+1})
-                    const int J = W.n_layers - 1;
-                    const int m_fmt = (y.m_panel >= 1 && y.m_panel <= J) ? p.act_fmt : UMNN_OPF_BF16;
-                    const int n_fmt = (y.n_panel >= 1 && y.n_panel <= J) ? p.act_fmt : UMNN_OPF_BF16;
-                    const uint32_t idesc = make_idesc_f32(256, y.n_width, m_fmt, n_fmt) | (1u << 15) | (1u << 16);
+                    const uint32_t idesc = make_idesc_bf16_f32(256, y.n_width) | (1u << 15) | (1u << 16);
                     // tiles hold [hi | lo] x [k8][W/16 core matrices]; the M tile is read 128 rows deep although only
                     // W/2 are staged (rows beyond feed accumulator rows nobody reads)
                     const uint32_t lbo_m = (uint32_t)(y.m_width / 16) * 128u, lbo_n = (uint32_t)(y.n_width / 16) * 128u;
@@ -815,10 +809,11 @@ int launch_backward_tc(const umnn_desc* d, const float* x0, const float* x, cons
     attr[0].val.clusterDim.z = 1;
 
     // fwd_blobs_fp16 != NULL: pass F re-evaluates the network with fp16 hi/lo operands (22 bits: far fewer
-    // LeakyReLU units flip side against the fp32 forward than with bf16's ~17) and writes A_1..A_J as fp16 panels,
-    // which pass W multiplies with the bf16 dz panels directly.  An activation beyond the fp16 range raises the
-    // flag; the whole backward is then repeated with bf16 operands by a second sequence of launches that are
-    // no-ops while the flag is clear.
+    // LeakyReLU units flip side against the fp32 forward than with bf16's ~17).  Its panels stay bf16 (split from
+    // the same fp32 activations): one tcgen05.mma cannot take an fp16 and a bf16 operand (illegal instruction on
+    // B200), and the dz panels need bf16's exponent range.  An activation beyond the fp16 range raises the flag;
+    // the whole backward is then repeated with bf16 operands by a second sequence of launches that are no-ops
+    // while the flag is clear.
     int* flag = reinterpret_cast<int*>(ws + B.off_flag);
     const int n_attempts = fwd_blobs_fp16 ? 2 : 1;
     if (fwd_blobs_fp16) UMNN_CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), s));
@@ -827,7 +822,6 @@ int launch_backward_tc(const umnn_desc* d, const float* x0, const float* x, cons
         const int* run_if = (fwd_blobs_fp16 && attempt == 1) ? flag : nullptr;
         g.run_if = run_if;
         w.run_if = run_if;
-        w.act_fmt = fp16_act ? UMNN_OPF_FP16 : UMNN_OPF_BF16;
         bool first = true;
         for (long long s0 = 0; s0 < n_slots; s0 += B.chunk_slots) {
             const long long cs = (n_slots - s0 < B.chunk_slots) ? (n_slots - s0) : B.chunk_slots;

@@ -43,15 +43,18 @@ template <bool NARROW>
 struct Shape {
     static constexpr int kEpiWarps = NARROW ? 8 : 16;        // 2 or 4 per TMEM lane quadrant
     static constexpr int kColGroups = kEpiWarps / 4;         // warp/4 handles 32-column pairs p % kColGroups == warp/4
-    static constexpr int kPrepWarps = 3;
+    static constexpr int kPrepWarps = NARROW ? 2 : 3;        // 2: 352 threads x 2 CTAs leave 88 registers per thread
     static constexpr int kMmaWarp = kEpiWarps + kPrepWarps;
-    static constexpr int kThreads = (kMmaWarp + 1) * 32;     // 640 / 384
+    static constexpr int kThreads = (kMmaWarp + 1) * 32;     // 640 / 352
     static constexpr int kEpiThreads = kEpiWarps * 32;
     static constexpr int kPrepThreads = kPrepWarps * 32;
     static constexpr uint32_t kRegion = NARROW ? kTcNarrowRegionCols : kTcRegionCols;
     static constexpr uint32_t kColP = 0, kColQ = kRegion;
     static constexpr uint32_t kTmemCols = 2 * kRegion;
     static constexpr int kCtasPerSm = NARROW ? 2 : 1;
+    // register budget: 65536 / (kCtasPerSm * kThreads), rounded down to the allocation unit of 8.  Given explicitly
+    // because __launch_bounds__(352, 2) budgets as if the CTA had 384 threads (80 registers, spills in the epilogue).
+    static constexpr int kMaxRegs = NARROW ? 88 : 96;
 };
 
 // barrier indices
@@ -101,14 +104,33 @@ __device__ __forceinline__ void emit16(const PanelRow& R, int col, const uint32_
     *reinterpret_cast<uint4*>(g1 + R.lo_off) = make_uint4(o[12], o[13], o[14], o[15]);
 }
 
+// One pair of activations -> hi / lo operand words in the launch's operand format (o_hi, o_lo) and, for pass F,
+// the bf16 hi / lo words of the panel (p_hi, p_lo; tcgen05 cannot mix an fp16 with a bf16 operand in one MMA, so
+// the panels that pass W multiplies with the bf16 dz panels are bf16 in every mode).  TRACK: keep the largest
+// |activation| converted to fp16 (networks whose hidden activation would swallow a NaN: ReLU).
+template <int OPF, bool EMIT, bool TRACK>
+__device__ __forceinline__ void split_pair(float a0, float a1, uint32_t& o_hi, uint32_t& o_lo, uint32_t& p_hi, uint32_t& p_lo,
+                                           float& amax) {
+    split_x2<OPF>(a0, a1, o_hi, o_lo);
+    if constexpr (EMIT) {
+        if constexpr (OPF == UMNN_OPF_BF16) { p_hi = o_hi; p_lo = o_lo; }
+        else split_bf16x2(a0, a1, p_hi, p_lo);
+    }
+    if constexpr (TRACK) amax = fmaxf(fmaxf(amax, fabsf(a0)), fabsf(a1));
+}
+
 template <int HIDDEN_ACT, bool EMIT, bool NARROW, int OPF>
-__global__ void __launch_bounds__(Shape<NARROW>::kThreads, Shape<NARROW>::kCtasPerSm)
+__global__ void __launch_bounds__(Shape<NARROW>::kThreads) __maxnreg__(Shape<NARROW>::kMaxRegs)
 cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
     using C = Shape<NARROW>;
     constexpr int kEpiWarps = C::kEpiWarps, kColGroups = C::kColGroups, kPrepWarps = C::kPrepWarps;
     constexpr int kMmaWarp = C::kMmaWarp, kThreads = C::kThreads, kEpiThreads = C::kEpiThreads, kPrepThreads = C::kPrepThreads;
     constexpr uint32_t kColP = C::kColP, kColQ = C::kColQ;
     static_assert(!(EMIT && NARROW), "pass F runs the wide shape");
+    // fp16 operands overflow above 65504.  With LeakyReLU the resulting inf / -inf pair turns every unit of the next
+    // layer -- and from there the row's output -- into NaN, which the finalize step sees for free; ReLU would map
+    // that NaN to 0, so ReLU networks track the largest converted value instead.
+    constexpr bool kTrack = (OPF == UMNN_OPF_FP16) && (HIDDEN_ACT == UMNN_ACT_RELU);
     // guarded re-run (see launch_forward_tc): nothing to do unless the first attempt raised the flag
     if (p.run_if != nullptr && *p.run_if == 0) return;
     extern __shared__ uint8_t smem_raw[];
@@ -347,16 +369,16 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
             const float xn = xnode[bu * kTcTile + r];
             const float* cv = cvec + ((size_t)bu * p.S.max_slots + lsrel[bu * kTcTile + r]) * L.npad1 + 16 * c16;
             const float* wx = w1x + 16 * c16;
-            uint32_t o[16], pre[16];
+            uint32_t o[16], ob[16], pre[16];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float v0 = fmaf(xn, wx[2 * i], cv[2 * i]), v1 = fmaf(xn, wx[2 * i + 1], cv[2 * i + 1]);
-                split_track<OPF>(hact<HIDDEN_ACT>(v0), hact<HIDDEN_ACT>(v1), o[i], o[8 + i], amax);
+                split_pair<OPF, EMIT, kTrack>(hact<HIDDEN_ACT>(v0), hact<HIDDEN_ACT>(v1), o[i], o[8 + i], ob[i], ob[8 + i], amax);
                 if (EMIT) { pre[2 * i] = __float_as_uint(v0); pre[2 * i + 1] = __float_as_uint(v1); }
             }
             tmem_st16(tbase + lane_sel + kColQ + 16u * c16, o);
             if (EMIT) {
-                emit16(panel_row(p.emit.a[1], cta_row0 + (long long)tile * kTcTile + r, L.npad1), 16 * c16, o);
+                emit16(panel_row(p.emit.a[1], cta_row0 + (long long)tile * kTcTile + r, L.npad1), 16 * c16, ob);
                 return sign_mask16(pre);
             }
             return 0u;
@@ -396,28 +418,31 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
                     tc_fence_after_sync();
                     const uint32_t taddr = tbase + lane_sel + col_d + 32u * pp;
                     const bool two = 32 * pp + 16 < y.npad;
-                    uint32_t v0[16], v1[16], o[16];
+                    uint32_t v0[16], v1[16], o[16], ob[16];
                     tmem_ld16(taddr, v0);
                     if (two) tmem_ld16(taddr + 16, v1);
                     tmem_ld_wait();
                     const long long pr = cta_row0 + (long long)t * kTcTile + r;
                     PanelRow prow;
-                    if (EMIT) prow = panel_row(p.emit.a[m + 2], pr, y.npad);
+                    if (EMIT) {
+                        prow = panel_row(p.emit.a[m + 2], pr, y.npad);
+                        // signs first: the accumulator registers die as they are converted below
+                        p.emit.mask[m + 2][pr * 8 + pp] = sign_mask16(v0) | (two ? sign_mask16(v1) << 4 : 0u);
+                    }
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
-                        split_track<OPF>(hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i + 1])),
-                                     o[i], o[8 + i], amax);
+                        split_pair<OPF, EMIT, kTrack>(hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i])),
+                                                      hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i + 1])), o[i], o[8 + i], ob[i], ob[8 + i], amax);
                     tmem_st16(taddr, o);
-                    if (EMIT) emit16(prow, 32 * pp, o);
+                    if (EMIT) emit16(prow, 32 * pp, ob);
                     if (two) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
-                            split_track<OPF>(hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i + 1])),
-                                         o[i], o[8 + i], amax);
+                            split_pair<OPF, EMIT, kTrack>(hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i])),
+                                                          hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i + 1])), o[i], o[8 + i], ob[i], ob[8 + i], amax);
                         tmem_st16(taddr + 16, o);
-                        if (EMIT) emit16(prow, 32 * pp + 16, o);
+                        if (EMIT) emit16(prow, 32 * pp + 16, ob);
                     }
-                    if (EMIT) p.emit.mask[m + 2][pr * 8 + pp] = sign_mask16(v0) | (two ? sign_mask16(v1) << 4 : 0u);
                     publish(m + 1, pp);
                 }
             }
@@ -452,14 +477,14 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
                         uint32_t o[16];
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
-                            split_track<OPF>(hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i + 1])),
-                                         o[i], o[8 + i], amax);
+                            split_bf16x2(hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i + 1])),
+                                         o[i], o[8 + i]);
                         emit16(prow, 32 * pp, o);
                         if (two) {
 #pragma unroll
                             for (int i = 0; i < 8; ++i)
-                                split_track<OPF>(hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i + 1])),
-                                             o[i], o[8 + i], amax);
+                                split_bf16x2(hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i + 1])),
+                                             o[i], o[8 + i]);
                             emit16(prow, 32 * pp + 16, o);
                         }
                         p.emit.mask[n_mma + 1][pr * 8 + pp] = sign_mask16(v0) | (two ? sign_mask16(v1) << 4 : 0u);
@@ -491,6 +516,8 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
                 for (int g = 1; g < kColGroups; ++g) vtot += part[(g - 1) * kTcTile + r];
                 if (EMIT) p.emit.v[cta_row0 + row0 + r] = node >= 0 ? vtot : 0.0f;
                 if (node >= 0) {
+                    // fp16 operands, LeakyReLU: an overflowed activation has made this row's output NaN (see kTrack)
+                    if (OPF == UMNN_OPF_FP16 && !kTrack && p.raise_flag != nullptr && !(fabsf(vtot) <= 3.0e38f)) *p.raise_flag = 1;
                     const float f = out_act(vtot, p.out_act);
                     if (node <= p.Q) {
                         fval[r] = f * tab_w[node];
@@ -532,8 +559,8 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[BAR_PREP_EMPTY + b]);
         }
-        // an activation beyond the fp16 range became inf in its operand: ask for the bf16 re-run
-        if (OPF == UMNN_OPF_FP16 && p.raise_flag != nullptr && amax > kFp16Max) *p.raise_flag = 1;
+        // ReLU networks: an activation beyond the fp16 range became inf in its operand -> ask for the bf16 re-run
+        if (kTrack && p.raise_flag != nullptr && amax > kFp16Max) *p.raise_flag = 1;
     }
 
     // ---------------------------------------------------------------- teardown
@@ -735,6 +762,30 @@ int launch_forward_tc(const umnn_desc* d, const float* x0, const float* x, const
                       : launch_tc_kernel<false, false, UMNN_OPF_FP16>(d->hidden_act, p, (int)n_cta, s);
     return narrow ? launch_tc_kernel<false, true, UMNN_OPF_BF16>(d->hidden_act, p, (int)n_cta, s)
                   : launch_tc_kernel<false, false, UMNN_OPF_BF16>(d->hidden_act, p, (int)n_cta, s);
+}
+
+// diagnostic behind umnn_tc_forward_occupancy: which shape serves the descriptor and how many CTAs of it one SM holds
+int tc_forward_occupancy(const umnn_desc* d, int extra_rows, int* narrow_out, int* ctas_per_sm) {
+    TcLayout L;
+    if (!make_tc_layout(d, &L, tc_two_segments())) {
+        set_error("tensor-core forward: shape not supported");
+        return UMNN_ERR_UNSUPPORTED;
+    }
+    const TcSmem S = make_tc_smem(L, d->nb_steps + 1 + extra_rows, d->nb_steps);
+    if (S.total > kTcMaxSmem) {
+        set_error("tensor-core forward: needs %u bytes of shared memory (max %zu)", S.total, kTcMaxSmem);
+        return UMNN_ERR_UNSUPPORTED;
+    }
+    const bool narrow = tc_narrow_enabled() && tc_layout_is_narrow(L) && S.total <= kTcNarrowMaxSmem;
+    const void* kern = narrow ? (const void*)cc_forward_tc_kernel<UMNN_ACT_LEAKY_RELU, false, true, UMNN_OPF_FP16>
+                              : (const void*)cc_forward_tc_kernel<UMNN_ACT_LEAKY_RELU, false, false, UMNN_OPF_FP16>;
+    UMNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
+    int n = 0;
+    UMNN_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, narrow ? Shape<true>::kThreads : Shape<false>::kThreads,
+                                                                S.total));
+    if (narrow_out) *narrow_out = narrow ? 1 : 0;
+    if (ctas_per_sm) *ctas_per_sm = n;
+    return 0;
 }
 
 // pass F of the tensor-core backward: the forward kernel over one chunk of slots with panel emission

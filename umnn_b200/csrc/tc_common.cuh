@@ -259,7 +259,7 @@ __device__ __forceinline__ void split_bf16x2(float even, float odd, uint32_t& hi
 }
 
 // fp16 hi/lo split:  v = hi + lo + O(2^-23 |v|) for 2^-3 <= |v| <= 65504 (absolute error <= 2^-25 below: lo is
-// subnormal there); |v| > 65504 overflows to inf (hi) -- callers track max |v| (split_track) and raise a flag.
+// subnormal there); |v| > 65504 overflows to inf (hi) and -inf / NaN (lo) -- see the guard in cc_forward_tc_kernel.
 __device__ __forceinline__ uint32_t pack_f16x2(float even, float odd) {
     uint32_t r;
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(odd), "f"(even));  // first source -> upper half
@@ -276,13 +276,6 @@ __device__ __forceinline__ void split_x2(float even, float odd, uint32_t& hi, ui
     else split_f16x2(even, odd, hi, lo);
 }
 
-// split + running max of |v| (fp16 only: lets the caller notice operands beyond the fp16 range; NaNs are ignored
-// by fmaxf, so a NaN input does not count as an overflow)
-template <int OPF>
-__device__ __forceinline__ void split_track(float even, float odd, uint32_t& hi, uint32_t& lo, float& amax) {
-    split_x2<OPF>(even, odd, hi, lo);
-    if constexpr (OPF == UMNN_OPF_FP16) amax = fmaxf(fmaxf(amax, fabsf(even)), fabsf(odd));
-}
 constexpr float kFp16Max = 65504.0f;
 
 // sign bits of 16 fp32 bit patterns, element 4k + j -> bit 8j + k (see mask_bitpos in tc_bwd_layout.cuh):

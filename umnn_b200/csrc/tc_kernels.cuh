@@ -8,8 +8,7 @@ namespace umnn {
 
 // panels written by pass F (EMIT) for one chunk of rows; index j = hidden layer (0 = network input)
 struct TcEmit {
-    uint8_t* a[UMNN_MAX_LAYERS];       // A_j panels (16-bit hi and lo interleaved per block, see tc_bwd_layout.cuh); A_0 is
-                                       // always bf16, A_1..A_J carry the operand format of the launch (bf16 or fp16)
+    uint8_t* a[UMNN_MAX_LAYERS];       // A_j panels (bf16 hi and lo interleaved per block, see tc_bwd_layout.cuh)
     uint32_t* mask[UMNN_MAX_LAYERS];   // [R_pad][8] sign bits per 32-column pair, j = 1..J
     float* v;                          // [R_pad] pre-output-activation
     int width[UMNN_MAX_LAYERS];        // panel widths P_j

@@ -159,6 +159,7 @@ int launch_pack_tc(const umnn_desc* d, const float* flat, void* packed, int opf,
 int launch_forward_tc(const umnn_desc* d, const float* x0, const float* x, const float* h, const void* packed,
                       const float* nodes, const float* weights, float* out, float* out_fx, float* out_fx0,
                       int opf, const int* run_if, int* raise_flag, cudaStream_t s);
+int tc_forward_occupancy(const umnn_desc* d, int extra_rows, int* narrow_out, int* ctas_per_sm);
 size_t tc_packed_bytes(const umnn_desc* d);
 // 0 if the tensor-core kernel can serve desc (with `extra_rows` = 0..2 extra rows per slot), else a reason string
 const char* tc_unsupported_reason(const umnn_desc* d, int extra_rows);

@@ -209,6 +209,17 @@ size_t umnn_workspace_bytes(const umnn_desc* d, int32_t for_backward) {
     return backward_fp32_workspace_bytes(d);
 }
 
+int umnn_tc_forward_occupancy(const umnn_desc* d, int32_t extra_rows, int32_t* narrow_shape, int32_t* ctas_per_sm) {
+    int rc = validate_desc(d);
+    if (rc) return rc;
+    int narrow = 0, n = 0;
+    rc = tc_forward_occupancy(d, extra_rows, &narrow, &n);
+    if (rc) return rc;
+    if (narrow_shape) *narrow_shape = narrow;
+    if (ctas_per_sm) *ctas_per_sm = n;
+    return 0;
+}
+
 int umnn_cc_forward(const umnn_desc* d, const float* x0, const float* x, const float* h, const void* params_packed,
                     const float* nodes, const float* weights, float* out_integral, float* out_f_at_x,
                     float* out_f_at_x0, void* workspace, size_t workspace_bytes, void* stream) {
