@@ -1,8 +1,8 @@
 #!/bin/bash
-# GPU visit: FP16x3 as the AUTO split (forward + backward re-evaluation, guarded bf16 re-runs), narrow kernel shape.
-# Usage (under gpurun): bash scripts/gpu_visit_r1g.sh [tag]
+# GPU visit (repeat after the mixed-operand fix): FP16x3 as the AUTO split (forward + backward re-evaluation, guarded bf16 re-runs), narrow kernel shape.
+# Usage (under gpurun): bash scripts/gpu_visit_r1h.sh [tag]
 set -u
-TAG=${1:-r1g}
+TAG=${1:-r1h}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/gpu.txt 2>&1
