@@ -37,7 +37,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
     if os.environ.get("UMNN_B200_TC_SPIN_LIMIT"):
-        # override the bound on mbarrier polling (default 2^27, see tc_common.cuh); 0 = spin forever
+        # override the bound on mbarrier waits in nanoseconds (default 2^32 ~ 4.3 s, see tc_common.cuh); 0 = wait forever
         flags += ["-DUMNN_TC_SPIN_LIMIT=" + os.environ["UMNN_B200_TC_SPIN_LIMIT"] + "LL"]
     cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + \
           [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH]

@@ -672,6 +672,8 @@ int launch_tc_kernel(int hidden_act, const TcParams& p, int n_cta, cudaStream_t 
     auto kern = hidden_act == UMNN_ACT_LEAKY_RELU ? cc_forward_tc_kernel<UMNN_ACT_LEAKY_RELU, EMIT, NARROW, OPF>
                                                   : cc_forward_tc_kernel<UMNN_ACT_RELU, EMIT, NARROW, OPF>;
     UMNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.S.total));
+    // two CTAs per SM need the full shared-memory carveout; without the hint the driver sizes it for one CTA
+    if (NARROW) UMNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)n_cta);
     cfg.blockDim = dim3(Shape<NARROW>::kThreads);
@@ -780,6 +782,7 @@ int tc_forward_occupancy(const umnn_desc* d, int extra_rows, int* narrow_out, in
     const void* kern = narrow ? (const void*)cc_forward_tc_kernel<UMNN_ACT_LEAKY_RELU, false, true, UMNN_OPF_FP16>
                               : (const void*)cc_forward_tc_kernel<UMNN_ACT_LEAKY_RELU, false, false, UMNN_OPF_FP16>;
     UMNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
+    if (narrow) UMNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int n = 0;
     UMNN_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, narrow ? Shape<true>::kThreads : Shape<false>::kThreads,
                                                                 S.total));

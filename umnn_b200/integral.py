@@ -390,30 +390,44 @@ def cc_integrate_host(integrand, x_host, h_host, nb_steps, want_fx=False, out=No
     bounds = [B * c // chunks for c in range(chunks + 1)]
     main = torch.cuda.current_stream(device)
     s_in, s_out = _side_streams(device)
-    s_in.wait_stream(main)
-    s_out.wait_stream(main)
     with torch.no_grad():
+        # device staging for the whole batch, allocated on the CURRENT stream (no per-chunk allocations on the side
+        # streams: their pools cannot recycle blocks while copies are in flight and fall back to cudaMalloc)
+        xd = torch.empty(x_host.shape, dtype=torch.float32, device=device)
+        hd = torch.empty(h_host.shape, dtype=torch.float32, device=device)
+        od = torch.empty(x_host.shape, dtype=torch.float32, device=device)
+        fd = torch.empty(x_host.shape, dtype=torch.float32, device=device) if want_fx else None
+        spec = kernel_route(integrand, xd, xd, hd, False)
+        if spec is None:
+            raise ValueError("cc_integrate_host needs float32 inputs and a recognised integrand within the "
+                             "kernel's limits")
+        s_in.wait_stream(main)       # whatever used these blocks before is ordered on the current stream
+        s_out.wait_stream(main)
+        uploaded = []
+        with torch.cuda.stream(s_in):
+            for c in range(chunks):
+                lo, hi = bounds[c], bounds[c + 1]
+                xd[lo:hi].copy_(x_host[lo:hi], non_blocking=True)
+                hd[lo:hi].copy_(h_host[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(s_in)
+                uploaded.append(ev)
         for c in range(chunks):
             lo, hi = bounds[c], bounds[c + 1]
-            with torch.cuda.stream(s_in):
-                xd = x_host[lo:hi].to(device, non_blocking=True)
-                hd = h_host[lo:hi].to(device, non_blocking=True)
-            main.wait_stream(s_in)
-            xd.record_stream(main)
-            hd.record_stream(main)
-            spec = kernel_route(integrand, xd, xd, hd, False)
-            if spec is None:
-                raise ValueError("cc_integrate_host needs float32 inputs and a recognised integrand within the "
-                                 "kernel's limits")
-            o, f, _ = kernel.cc_forward(spec, None, xd, hd, nb_steps, want_fx=want_fx, precision=precision)
-            s_out.wait_stream(main)
+            main.wait_event(uploaded[c])
+            kernel.cc_forward(spec, None, xd[lo:hi], hd[lo:hi], nb_steps, want_fx=want_fx, precision=precision,
+                              out=od[lo:hi], fx_out=None if fd is None else fd[lo:hi])
+            done = torch.cuda.Event()
+            done.record(main)
             with torch.cuda.stream(s_out):
-                out[lo:hi].copy_(o, non_blocking=True)
-                o.record_stream(s_out)
+                s_out.wait_event(done)
+                out[lo:hi].copy_(od[lo:hi], non_blocking=True)
                 if want_fx:
-                    fx_out[lo:hi].copy_(f, non_blocking=True)
-                    f.record_stream(s_out)
-    main.wait_stream(s_out)
+                    fx_out[lo:hi].copy_(fd[lo:hi], non_blocking=True)
+        # the staging tensors are released when this function returns: everything that touches them is ordered
+        # before whatever the current stream does next
+        main.wait_stream(s_in)
+        main.wait_stream(s_out)
     return out, (fx_out if want_fx else None)
 
 

@@ -96,10 +96,12 @@ def make_desc(spec: KernelSpec, x: torch.Tensor, nb_steps: int, precision: Optio
 
 
 def cc_forward(spec: KernelSpec, x0: Optional[torch.Tensor], x: torch.Tensor, h: torch.Tensor, nb_steps: int,
-               want_fx: bool = False, want_fx0: bool = False, precision: Optional[int] = None):
+               want_fx: bool = False, want_fx0: bool = False, precision: Optional[int] = None,
+               out: Optional[torch.Tensor] = None, fx_out: Optional[torch.Tensor] = None):
     """One fused launch: (integral, f(x,h) or None, f(x0,h) or None), each [B, Dx].
 
     Replaces integrate(...) + IntegrandNetwork.forward of the reference (see include/umnn_b200.h).
+    `out` / `fx_out`: optional preallocated contiguous float32 results on x's device (written in place).
     """
     L = _native.lib()
     x = _as_f32c(x)
@@ -112,8 +114,12 @@ def cc_forward(spec: KernelSpec, x0: Optional[torch.Tensor], x: torch.Tensor, h:
     if x0 is not None and x0.shape != x.shape:
         raise ValueError("x0 and x must have the same shape")
     dev = x.device
-    out = torch.empty_like(x)
-    fx = torch.empty_like(x) if want_fx else None
+    for t in (out, fx_out):
+        if t is not None and not (t.shape == x.shape and t.dtype == torch.float32 and t.is_contiguous() and t.device == dev):
+            raise ValueError("cc_forward: out / fx_out must be contiguous float32 tensors shaped like x on x's device")
+    if out is None:
+        out = torch.empty_like(x)
+    fx = (fx_out if fx_out is not None else torch.empty_like(x)) if want_fx else None
     fx0 = torch.empty_like(x) if want_fx0 else None
     if B == 0:
         return out, fx, fx0
