@@ -53,6 +53,21 @@ extern "C" {
 enum { UMNN_LAYOUT_STRIDED_D = 0, UMNN_LAYOUT_CONTIG = 1 };
 enum { UMNN_ACT_RELU = 0, UMNN_ACT_LEAKY_RELU = 1 };           /* hidden; leaky slope 0.01 */
 enum { UMNN_OUT_ELU_PLUS_1 = 0, UMNN_OUT_SIGMOID = 1 };        /* UMNNMAF.py:11-19 */
+/*
+ * Arithmetic of the hidden-to-hidden layers (layer 1, the output layer, activations and the quadrature sum are
+ * fp32 on CUDA cores in every mode):
+ *   UMNN_PREC_FP32    FFMA kernel, any shape within UMNN_MAX_*.
+ *   UMNN_PREC_BF16X3  tcgen05 tensor cores, operands split into bf16 hi + lo (3 MMAs per product, fp32 accumulate,
+ *                     ~17 bits per operand, fp32 exponent range).
+ *   UMNN_PREC_FP16X3  same scheme with fp16 hi + lo operands (22 bits per operand: integrals within 3e-6 of the
+ *                     fp32 reference where BF16X3 reaches 2e-5).  fp16 overflows above 65504: the kernel raises a
+ *                     device flag (in the forward workspace) when an activation leaves that range and a second
+ *                     launch of the BF16X3 kernel -- a no-op while the flag is clear -- recomputes the call, so the
+ *                     result is never worse than BF16X3 and the host never has to look.
+ *   UMNN_PREC_AUTO    FP16X3 (or BF16X3 if the environment variable UMNN_B200_AUTO_TC=bf16x3 is set) where the
+ *                     tensor-core kernel serves the shape (>= 2 hidden layers, widths <= 254, parameters within
+ *                     shared memory), else FP32.
+ */
 enum { UMNN_PREC_FP32 = 0, UMNN_PREC_BF16X3 = 1, UMNN_PREC_AUTO = 2, UMNN_PREC_FP16X3 = 3 };
 
 enum {
@@ -102,7 +117,10 @@ UMNN_API int64_t umnn_param_count(const umnn_desc* desc);
 UMNN_API size_t umnn_packed_params_bytes(const umnn_desc* desc);
 UMNN_API int umnn_pack_params(const umnn_desc* desc, const float* flat_params, void* params_packed, void* stream);
 
-/* Scratch the forward / backward entry points need for desc (0 is possible). */
+/*
+ * Scratch the forward (for_backward = 0) / backward (1) entry points need for desc (0 is possible).  The forward
+ * needs 256 bytes for UMNN_PREC_FP16X3 (the overflow flag of the guarded re-run) and nothing otherwise.
+ */
 UMNN_API size_t umnn_workspace_bytes(const umnn_desc* desc, int32_t for_backward);
 
 /*
@@ -120,6 +138,8 @@ UMNN_API size_t umnn_workspace_bytes(const umnn_desc* desc, int32_t for_backward
  *   out_integral  [B][Dx]
  *   out_f_at_x    [B][Dx] or NULL;  out_f_at_x0 [B][Dx] or NULL
  *   nodes, weights  device tables of Q+1 floats (umnn_cc_tables / compute_cc_weights)
+ *   workspace     umnn_workspace_bytes(desc, 0) bytes, or NULL (UMNN_PREC_FP16X3 then runs unguarded: an activation
+ *                 beyond the fp16 range surfaces as NaN)
  */
 UMNN_API int umnn_cc_forward(const umnn_desc* desc, const float* x0, const float* x, const float* h,
                     const void* params_packed, const float* nodes, const float* weights,
@@ -147,9 +167,10 @@ UMNN_API int umnn_tc_forward_occupancy(const umnn_desc* desc, int32_t extra_rows
  * integrate(compute_grad=True) :66-80, computeIntegrand :83-94 (and NeuralIntegral.py:47-64,69-75,90-99).
  *   d_params [P] is OVERWRITTEN (not accumulated); any of d_x0, d_x, d_h, d_params may be NULL.
  * desc.precision selects the path (and must be the precision params_packed was packed with):
- * UMNN_PREC_BF16X3 / AUTO = three tensor-core passes per chunk of rows (forward re-evaluation with operand
- * emission, dgrad with transposed weights, split-K weight-gradient GEMM), UMNN_PREC_FP32 = fused FFMA kernel
- * + FFMA split-K GEMM.  workspace must hold umnn_workspace_bytes(desc, 1) bytes (operand panels of one chunk;
+ * UMNN_PREC_BF16X3 / FP16X3 / AUTO = three tensor-core passes per chunk of rows (forward re-evaluation with operand
+ * emission, dgrad with transposed weights, split-K weight-gradient GEMM; FP16X3 re-evaluates with fp16 operands
+ * and repeats the passes with bf16 operands if an activation left the fp16 range), UMNN_PREC_FP32 = fused FFMA
+ * kernel + FFMA split-K GEMM.  workspace must hold umnn_workspace_bytes(desc, 1) bytes (operand panels of one chunk;
  * the batch is processed in chunks of whole slots).  A shape the tensor-core backward cannot serve returns
  * UMNN_ERR_UNSUPPORTED (retry with UMNN_PREC_FP32).  Deterministic (fixed reduction order).
  */

@@ -43,18 +43,17 @@ template <bool NARROW>
 struct Shape {
     static constexpr int kEpiWarps = NARROW ? 8 : 16;        // 2 or 4 per TMEM lane quadrant
     static constexpr int kColGroups = kEpiWarps / 4;         // warp/4 handles 32-column pairs p % kColGroups == warp/4
-    static constexpr int kPrepWarps = NARROW ? 2 : 3;        // 2: 352 threads x 2 CTAs leave 88 registers per thread
+    static constexpr int kPrepWarps = 3;
     static constexpr int kMmaWarp = kEpiWarps + kPrepWarps;
-    static constexpr int kThreads = (kMmaWarp + 1) * 32;     // 640 / 352
+    static constexpr int kThreads = (kMmaWarp + 1) * 32;     // 640 / 384
     static constexpr int kEpiThreads = kEpiWarps * 32;
     static constexpr int kPrepThreads = kPrepWarps * 32;
     static constexpr uint32_t kRegion = NARROW ? kTcNarrowRegionCols : kTcRegionCols;
     static constexpr uint32_t kColP = 0, kColQ = kRegion;
     static constexpr uint32_t kTmemCols = 2 * kRegion;
+    // NARROW: 12 warps x 2 CTAs -> 80 registers per thread.  (Registers are handed out to groups of 4 warps: an
+    // 11-warp CTA with 88 registers is budgeted as 12 warps and only ONE of them fits an SM -- measured.)
     static constexpr int kCtasPerSm = NARROW ? 2 : 1;
-    // register budget: 65536 / (kCtasPerSm * kThreads), rounded down to the allocation unit of 8.  Given explicitly
-    // because __launch_bounds__(352, 2) budgets as if the CTA had 384 threads (80 registers, spills in the epilogue).
-    static constexpr int kMaxRegs = NARROW ? 88 : 96;
 };
 
 // barrier indices
@@ -120,7 +119,7 @@ __device__ __forceinline__ void split_pair(float a0, float a1, uint32_t& o_hi, u
 }
 
 template <int HIDDEN_ACT, bool EMIT, bool NARROW, int OPF>
-__global__ void __launch_bounds__(Shape<NARROW>::kThreads) __maxnreg__(Shape<NARROW>::kMaxRegs)
+__global__ void __launch_bounds__(Shape<NARROW>::kThreads, Shape<NARROW>::kCtasPerSm)
 cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
     using C = Shape<NARROW>;
     constexpr int kEpiWarps = C::kEpiWarps, kColGroups = C::kColGroups, kPrepWarps = C::kPrepWarps;
@@ -134,7 +133,9 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
     // guarded re-run (see launch_forward_tc): nothing to do unless the first attempt raised the flag
     if (p.run_if != nullptr && *p.run_if == 0) return;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte aligned base, by pointer arithmetic on the __shared__ array so that the compiler keeps the
+    // address space (LDS/STS instead of generic LD/ST on every table and scratch access)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
