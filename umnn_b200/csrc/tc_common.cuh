@@ -90,7 +90,7 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 #ifndef UMNN_TC_SPIN_LIMIT
 #define UMNN_TC_SPIN_LIMIT (1LL << 32)
 #endif
-__device__ __noinline__ void mbar_wait_expired(int tag, uint32_t parity) {
+static __device__ __noinline__ void mbar_wait_expired(int tag, uint32_t parity) {
     printf("mbar_wait timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x, (int)threadIdx.x, parity);
     __trap();
 }
