@@ -1,0 +1,26 @@
+"""Build experiment variants of the library (compile-time switches of the tensor-core kernels) under
+umnn_b200/variants/; select one at run time with UMNN_B200_LIB=<path>."""
+import os
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+from umnn_b200 import build as B   # noqa: E402
+
+VARIANTS = {
+    "lds_count": [],                                                         # product: LDS, hint, clock every 4096 polls
+    "gen_count": ["-DUMNN_TC_SMEM_GENERIC=1"],
+    "lds_timer": ["-DUMNN_TC_WAIT_STYLE=1"],
+    "gen_timer": ["-DUMNN_TC_SMEM_GENERIC=1", "-DUMNN_TC_WAIT_STYLE=1"],    # = visit r1i
+    "lds_plain": ["-DUMNN_TC_WAIT_STYLE=2", "-DUMNN_TC_WAIT_HINT=0"],
+    "gen_plain": ["-DUMNN_TC_SMEM_GENERIC=1", "-DUMNN_TC_WAIT_STYLE=2", "-DUMNN_TC_WAIT_HINT=0"],   # = before this change
+    "lds_plain_hint": ["-DUMNN_TC_WAIT_STYLE=2"],
+}
+
+if __name__ == "__main__":
+    out_dir = os.path.join(REPO, "umnn_b200", "variants")
+    os.makedirs(out_dir, exist_ok=True)
+    for name in (sys.argv[1:] or VARIANTS):
+        path = os.path.join(out_dir, f"libumnn_b200_{name}.so")
+        B.build(force=True, extra_flags=VARIANTS[name], out=path)
+        print(path, flush=True)

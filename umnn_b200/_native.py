@@ -10,7 +10,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libumnn_b200.so")
+# UMNN_B200_LIB: load an experiment variant of the library (scripts/build_variants.py) instead of the product build
+LIB_PATH = os.environ.get("UMNN_B200_LIB") or os.path.join(_HERE, "libumnn_b200.so")
 
 UMNN_ABI_VERSION = 1
 UMNN_MAX_LAYERS = 8

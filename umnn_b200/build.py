@@ -31,22 +31,23 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source into one shared library; returns its path."""
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str = LIB_PATH) -> str:
+    """Compile every CUDA source into one shared library; returns its path.  `extra_flags` / `out` build an
+    experiment variant next to the product library (see scripts/build_variants.py)."""
+    if not force and not extra_flags and out == LIB_PATH and not _stale():
         return LIB_PATH
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
     if os.environ.get("UMNN_B200_TC_SPIN_LIMIT"):
         # override the bound on mbarrier waits in nanoseconds (default 2^32 ~ 4.3 s, see tc_common.cuh); 0 = wait forever
         flags += ["-DUMNN_TC_SPIN_LIMIT=" + os.environ["UMNN_B200_TC_SPIN_LIMIT"] + "LL"]
-    cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH]
+    cmd = [_nvcc()] + flags + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + \
+          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libumnn_b200.so")
-    return LIB_PATH
+    return out
 
 
 if __name__ == "__main__":

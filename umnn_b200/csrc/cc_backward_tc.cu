@@ -90,7 +90,11 @@ __global__ void __launch_bounds__(kThreads, 1) cc_dgrad_tc_kernel(const __grid_c
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte aligned base, by pointer arithmetic on the __shared__ array so that the compiler keeps the
     // address space (LDS/STS instead of generic LD/ST on every table and scratch access)
+#if defined(UMNN_TC_SMEM_GENERIC) && UMNN_TC_SMEM_GENERIC
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+#else
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+#endif
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
     const TcDgradLayout& L = p.L;
@@ -481,7 +485,11 @@ __global__ void __launch_bounds__(kWThreads, 1) cc_wgrad_tc_kernel(const __grid_
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte aligned base, by pointer arithmetic on the __shared__ array so that the compiler keeps the
     // address space (LDS/STS instead of generic LD/ST on every table and scratch access)
+#if defined(UMNN_TC_SMEM_GENERIC) && UMNN_TC_SMEM_GENERIC
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+#else
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+#endif
     __shared__ __align__(8) uint64_t full[kWMaxStages], empty[kWMaxStages], done, peer_ready[kWMaxStages];
     const int kWStages = p.n_stages;
     __shared__ uint32_t holder;

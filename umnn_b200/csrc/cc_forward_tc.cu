@@ -135,7 +135,11 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte aligned base, by pointer arithmetic on the __shared__ array so that the compiler keeps the
     // address space (LDS/STS instead of generic LD/ST on every table and scratch access)
+#if defined(UMNN_TC_SMEM_GENERIC) && UMNN_TC_SMEM_GENERIC
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+#else
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+#endif
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
@@ -784,9 +788,23 @@ int tc_forward_occupancy(const umnn_desc* d, int extra_rows, int* narrow_out, in
                               : (const void*)cc_forward_tc_kernel<UMNN_ACT_LEAKY_RELU, false, false, UMNN_OPF_FP16>;
     UMNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
     if (narrow) UMNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    int n = 0;
-    UMNN_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, narrow ? Shape<true>::kThreads : Shape<false>::kThreads,
-                                                                S.total));
+    // the kernel is launched as clusters of 2: ask how many clusters the device holds at once
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2048);
+    cfg.blockDim = dim3(narrow ? Shape<true>::kThreads : Shape<false>::kThreads);
+    cfg.dynamicSmemBytes = S.total;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n_clusters = 0, dev = 0, n_sm = 0;
+    UMNN_CUDA_TRY(cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfg));
+    UMNN_CUDA_TRY(cudaGetDevice(&dev));
+    UMNN_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    const int n = n_sm > 0 ? (2 * n_clusters) / n_sm : 0;
     if (narrow_out) *narrow_out = narrow ? 1 : 0;
     if (ctas_per_sm) *ctas_per_sm = n;
     return 0;

@@ -56,8 +56,12 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 // does not change how often a waiting warp polls -- try_wait returns after a short hardware time-out either way
 // (1.4e9 polls per 53 M rows with and without it) -- so the wait loops below keep the per-poll work minimal.
 constexpr uint32_t kMbarSuspendHintNs = 0x989680u;   // 10 ms, the value CUTLASS passes
+#ifndef UMNN_TC_WAIT_HINT
+#define UMNN_TC_WAIT_HINT 1
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
+#if UMNN_TC_WAIT_HINT
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
@@ -65,6 +69,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity), "r"(kMbarSuspendHintNs)
         : "memory");
+#else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+#endif
     return ok != 0;
 }
 // acquire at cluster scope: needed when the arrivals come from the peer CTA
@@ -94,8 +107,25 @@ static __device__ __noinline__ void mbar_wait_expired(int tag, uint32_t parity) 
     printf("mbar_wait timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x, (int)threadIdx.x, parity);
     __trap();
 }
+// UMNN_TC_WAIT_STYLE (experiment switch): 0 = poll, clock every 4096 polls; 1 = clock after every failed poll;
+// 2 = poll count only (2^27 polls), no clock
+#ifndef UMNN_TC_WAIT_STYLE
+#define UMNN_TC_WAIT_STYLE 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
-#if UMNN_TC_SPIN_LIMIT
+#if !UMNN_TC_SPIN_LIMIT
+    (void)tag;
+    while (!mbar_try_wait(bar, parity)) {}
+#elif UMNN_TC_WAIT_STYLE == 1
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = global_timer_ns();
+    while (!mbar_try_wait(bar, parity))
+        if (global_timer_ns() - t0 > (unsigned long long)(UMNN_TC_SPIN_LIMIT)) mbar_wait_expired(tag, parity);
+#elif UMNN_TC_WAIT_STYLE == 2
+    for (int i = 0; i < (1 << 27); ++i)
+        if (mbar_try_wait(bar, parity)) return;
+    mbar_wait_expired(tag, parity);
+#else
     unsigned long long t0 = 0;
     for (uint32_t n = 1; !mbar_try_wait(bar, parity); ++n) {
         if ((n & 0xFFFu) == 0) {
@@ -104,9 +134,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
             else if (now - t0 > (unsigned long long)(UMNN_TC_SPIN_LIMIT)) mbar_wait_expired(tag, parity);
         }
     }
-#else
-    (void)tag;
-    while (!mbar_try_wait(bar, parity)) {}
 #endif
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int tag = 0) {
