@@ -149,8 +149,10 @@ UMNN_API int umnn_cc_forward(const umnn_desc* desc, const float* x0, const float
 /*
  * Diagnostic (needs a CUDA device): which shape of the tensor-core forward kernel serves desc with `extra_rows`
  * (0..2) point evaluations per slot -- narrow_shape = 1: two CTAs per SM with 128-column tensor-memory regions
- * (every padded hidden width <= 128), 0: one CTA per SM with 256-column regions -- and how many CTAs of it the
- * occupancy calculator places on one SM.  UMNN_ERR_UNSUPPORTED if the tensor-core kernel cannot serve the shape.
+ * (every padded hidden width <= 128), 0: one CTA per SM with 256-column regions -- and how many CTAs of it per SM
+ * cudaOccupancyMaxActiveClusters accounts for (informational: for the narrow shape the calculator answers 1 while
+ * the hardware co-schedules 2).  UMNN_ERR_UNSUPPORTED if the tensor-core kernel cannot serve
+ * the shape.
  */
 UMNN_API int umnn_tc_forward_occupancy(const umnn_desc* desc, int32_t extra_rows, int32_t* narrow_shape,
                               int32_t* ctas_per_sm);

@@ -8,9 +8,9 @@ sys.path.insert(0, REPO)
 from umnn_b200 import build as B   # noqa: E402
 
 VARIANTS = {
-    "lds_count": [],                                                         # product: LDS, hint, clock every 4096 polls
-    "gen_count": ["-DUMNN_TC_SMEM_GENERIC=1"],
-    "lds_timer": ["-DUMNN_TC_WAIT_STYLE=1"],
+    "lds_count": ["-DUMNN_TC_WAIT_STYLE=0"],                                 # LDS, hint, clock every 4096 polls
+    "gen_count": ["-DUMNN_TC_SMEM_GENERIC=1", "-DUMNN_TC_WAIT_STYLE=0"],
+    "lds_timer": ["-DUMNN_TC_WAIT_STYLE=1"],                                 # = product build
     "gen_timer": ["-DUMNN_TC_SMEM_GENERIC=1", "-DUMNN_TC_WAIT_STYLE=1"],    # = visit r1i
     "lds_plain": ["-DUMNN_TC_WAIT_STYLE=2", "-DUMNN_TC_WAIT_HINT=0"],
     "gen_plain": ["-DUMNN_TC_SMEM_GENERIC=1", "-DUMNN_TC_WAIT_STYLE=2", "-DUMNN_TC_WAIT_HINT=0"],   # = before this change

@@ -102,18 +102,54 @@ def test_native_library_is_the_loaded_path():
     assert "libumnn_b200.so" in loaded
 
 
-@pytest.mark.parametrize("hidden,narrow,ctas", [([100, 100, 100, 100], 1, 2), ([100, 50, 50, 50, 50], 1, 2),
-                                                 ([126, 126], 1, 2), ([127, 127], 0, 1), ([200, 200, 200], 0, 1)])
-def test_narrow_shape_runs_two_ctas_per_sm(hidden, narrow, ctas):
-    """Integrands whose padded widths fit 128 tensor-memory columns get the narrow kernel shape, and the hardware
-    really holds two of its CTAs per SM (registers, shared memory and threads all allow it)."""
+@pytest.mark.parametrize("hidden,narrow", [([100, 100, 100, 100], 1), ([100, 50, 50, 50, 50], 1), ([126, 126], 1),
+                                           ([127, 127], 0), ([200, 200, 200], 0)])
+def test_narrow_shape_selection(hidden, narrow):
+    """Integrands whose padded widths fit 128 tensor-memory columns get the narrow kernel shape (two CTAs per SM)."""
     import ctypes
     from umnn_b200 import _native
     desc = _native.make_desc(_native.LAYOUT_STRIDED_D, 1000, 6, 30, [31] + hidden + [1], _native.ACT_LEAKY_RELU,
                              _native.OUT_ELU_PLUS_1, 50, _native.PREC_AUTO)
     is_narrow, n = ctypes.c_int32(-1), ctypes.c_int32(-1)
     _native.check(_native.lib().umnn_tc_forward_occupancy(desc, 1, ctypes.byref(is_narrow), ctypes.byref(n)))
-    assert (is_narrow.value, n.value) == (narrow, ctas)
+    assert is_narrow.value == narrow and n.value >= 1
+
+
+def test_narrow_shape_really_overlaps_two_tiles_per_sm():
+    """The occupancy calculators (CUDA runtime, ncu) report one cluster per SM pair for the narrow shape, yet the
+    hardware co-schedules two (ncu: 23.6 of 64 warps active = 2 x 12): the evidence that counts is the speed-up over
+    the same kernel with one CTA per SM (measured 1.40x on config 5; an 11-warp variant that did NOT fit twice ran at
+    0.70x).  Both shapes give the same integral up to summation order."""
+    from umnn_b200 import cc_integrate
+    spec = orc.MLPSpec((31, 100, 50, 50, 50, 50, 1))
+    flat = orc.synth_params(spec, 0, 1.0)
+    net = _net_for(spec, flat, "strided", 784).eval()
+    d = _dev()
+    g = torch.Generator(device=d).manual_seed(4)
+    x = 2 * torch.randn(100, 784, device=d, generator=g)
+    h = torch.randn(100, 30 * 784, device=d, generator=g)
+    res = {}
+    prev = os.environ.get("UMNN_B200_TC_NARROW")
+    try:
+        for narrow in ("1", "0"):
+            os.environ["UMNN_B200_TC_NARROW"] = narrow
+            for _ in range(3):
+                out = cc_integrate(net, None, x, h, 50, want_fx=True)[0]
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(20):
+                cc_integrate(net, None, x, h, 50, want_fx=True)
+            e.record()
+            torch.cuda.synchronize()
+            res[narrow] = (s.elapsed_time(e) / 20, out.cpu().numpy())
+    finally:
+        if prev is None:
+            os.environ.pop("UMNN_B200_TC_NARROW", None)
+        else:
+            os.environ["UMNN_B200_TC_NARROW"] = prev
+    assert rel_err(res["1"][1], res["0"][1]) < 2e-6
+    assert res["0"][0] / res["1"][0] > 1.15, (res["1"][0], res["0"][0])
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)

@@ -52,9 +52,8 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// try_wait with a suspend-time hint (the value CUTLASS passes).  Measured on B200 (ncu, forward kernel): the hint
-// does not change how often a waiting warp polls -- try_wait returns after a short hardware time-out either way
-// (1.4e9 polls per 53 M rows with and without it) -- so the wait loops below keep the per-poll work minimal.
+// try_wait with a suspend-time hint (the value CUTLASS passes): ptxas turns it into TRYWAIT + NANOSLEEP.SYNCS +
+// re-probe, i.e. the warp sleeps on the barrier between probes instead of spinning.
 constexpr uint32_t kMbarSuspendHintNs = 0x989680u;   // 10 ms, the value CUTLASS passes
 #ifndef UMNN_TC_WAIT_HINT
 #define UMNN_TC_WAIT_HINT 1
@@ -107,10 +106,13 @@ static __device__ __noinline__ void mbar_wait_expired(int tag, uint32_t parity) 
     printf("mbar_wait timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x, (int)threadIdx.x, parity);
     __trap();
 }
-// UMNN_TC_WAIT_STYLE (experiment switch): 0 = poll, clock every 4096 polls; 1 = clock after every failed poll;
-// 2 = poll count only (2^27 polls), no clock
+// UMNN_TC_WAIT_STYLE: 1 (default) = read the clock after every failed poll; 0 = clock every 4096 polls; 2 = poll
+// count only (2^27 polls), no clock.  A/B on one B200 (scripts/gpu_visit_r1k.sh, ms per step, config 4 at
+// B = 8192 / config 3 / config 5): style 1 24.94 / 1.413 / 1.281, style 0 25.05 / 1.426 / 1.290, style 2 with or
+// without the hint 25.67 / 1.487 / 1.358 -- the slower the idle warps poll, the more issue slots and LSU bandwidth
+// the working warps get (the hint lets ptxas put a NANOSLEEP.SYNCS between two probes; the clock read adds to it).
 #ifndef UMNN_TC_WAIT_STYLE
-#define UMNN_TC_WAIT_STYLE 0
+#define UMNN_TC_WAIT_STYLE 1
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
 #if !UMNN_TC_SPIN_LIMIT
