@@ -15,6 +15,11 @@ VARIANTS = {
     "lds_plain": ["-DUMNN_TC_WAIT_STYLE=2", "-DUMNN_TC_WAIT_HINT=0"],
     "gen_plain": ["-DUMNN_TC_SMEM_GENERIC=1", "-DUMNN_TC_WAIT_STYLE=2", "-DUMNN_TC_WAIT_HINT=0"],   # = before this change
     "lds_plain_hint": ["-DUMNN_TC_WAIT_STYLE=2"],
+    "lds_sleep20": ["-DUMNN_TC_WAIT_STYLE=3", "-DUMNN_TC_WAIT_SLEEP_NS=20"],
+    "lds_sleep50": ["-DUMNN_TC_WAIT_STYLE=3", "-DUMNN_TC_WAIT_SLEEP_NS=50"],
+    "lds_sleep100": ["-DUMNN_TC_WAIT_STYLE=3", "-DUMNN_TC_WAIT_SLEEP_NS=100"],
+    "lds_sleep200": ["-DUMNN_TC_WAIT_STYLE=3", "-DUMNN_TC_WAIT_SLEEP_NS=200"],
+    "lds_sleep50_nohint": ["-DUMNN_TC_WAIT_STYLE=3", "-DUMNN_TC_WAIT_SLEEP_NS=50", "-DUMNN_TC_WAIT_HINT=0"],
 }
 
 if __name__ == "__main__":

@@ -114,6 +114,9 @@ static __device__ __noinline__ void mbar_wait_expired(int tag, uint32_t parity) 
 #ifndef UMNN_TC_WAIT_STYLE
 #define UMNN_TC_WAIT_STYLE 1
 #endif
+#ifndef UMNN_TC_WAIT_SLEEP_NS
+#define UMNN_TC_WAIT_SLEEP_NS 50
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
 #if !UMNN_TC_SPIN_LIMIT
     (void)tag;
@@ -127,6 +130,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
     for (int i = 0; i < (1 << 27); ++i)
         if (mbar_try_wait(bar, parity)) return;
     mbar_wait_expired(tag, parity);
+#elif UMNN_TC_WAIT_STYLE == 3
+    // explicit back-off of UMNN_TC_WAIT_SLEEP_NS between probes, clock every 1024 probes
+    if (mbar_try_wait(bar, parity)) return;
+    unsigned long long t0 = 0;
+    for (uint32_t n = 1; !mbar_try_wait(bar, parity); ++n) {
+        __nanosleep(UMNN_TC_WAIT_SLEEP_NS);
+        if ((n & 0x3FFu) == 0) {
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > (unsigned long long)(UMNN_TC_SPIN_LIMIT)) mbar_wait_expired(tag, parity);
+        }
+    }
 #else
     unsigned long long t0 = 0;
     for (uint32_t n = 1; !mbar_try_wait(bar, parity); ++n) {
