@@ -1,9 +1,9 @@
 #!/bin/bash
 # GPU visit: full check of the round's state -- parity suite, smoke, bench lines for the five configurations and the
 # reference arm, launch lists, ncu full captures (wide forward, narrow forward, the three backward passes), flow bench.
-# Usage (under gpurun): bash scripts/gpu_visit_r1j.sh [tag]
+# Usage (under gpurun): bash scripts/gpu_visit_r1m.sh [tag]
 set -u
-TAG=${1:-r1j}
+TAG=${1:-r1m}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/gpu.txt 2>&1

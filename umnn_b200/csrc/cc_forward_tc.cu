@@ -375,11 +375,22 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
             const float* cv = cvec + ((size_t)bu * p.S.max_slots + lsrel[bu * kTcTile + r]) * L.npad1 + 16 * c16;
             const float* wx = w1x + 16 * c16;
             uint32_t o[16], ob[16], pre[16];
+            // 16-byte shared loads (both tables are 64-byte aligned per 16 columns; the lanes of a warp read the same
+            // or two different slots, i.e. broadcasts)
+            const float4* cv4 = reinterpret_cast<const float4*>(cv);
+            const float4* wx4 = reinterpret_cast<const float4*>(wx);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float v0 = fmaf(xn, wx[2 * i], cv[2 * i]), v1 = fmaf(xn, wx[2 * i + 1], cv[2 * i + 1]);
-                split_pair<OPF, EMIT, kTrack>(hact<HIDDEN_ACT>(v0), hact<HIDDEN_ACT>(v1), o[i], o[8 + i], ob[i], ob[8 + i], amax);
-                if (EMIT) { pre[2 * i] = __float_as_uint(v0); pre[2 * i + 1] = __float_as_uint(v1); }
+            for (int j = 0; j < 4; ++j) {
+                const float4 c = cv4[j], w = wx4[j];
+                const float v0 = fmaf(xn, w.x, c.x), v1 = fmaf(xn, w.y, c.y), v2 = fmaf(xn, w.z, c.z), v3 = fmaf(xn, w.w, c.w);
+                split_pair<OPF, EMIT, kTrack>(hact<HIDDEN_ACT>(v0), hact<HIDDEN_ACT>(v1), o[2 * j], o[8 + 2 * j], ob[2 * j],
+                                              ob[8 + 2 * j], amax);
+                split_pair<OPF, EMIT, kTrack>(hact<HIDDEN_ACT>(v2), hact<HIDDEN_ACT>(v3), o[2 * j + 1], o[9 + 2 * j], ob[2 * j + 1],
+                                              ob[9 + 2 * j], amax);
+                if (EMIT) {
+                    pre[4 * j] = __float_as_uint(v0); pre[4 * j + 1] = __float_as_uint(v1);
+                    pre[4 * j + 2] = __float_as_uint(v2); pre[4 * j + 3] = __float_as_uint(v3);
+                }
             }
             tmem_st16(tbase + lane_sel + kColQ + 16u * c16, o);
             if (EMIT) {
@@ -468,12 +479,24 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
                     tmem_ld16(taddr, v0);
                     if (two) tmem_ld16(taddr + 16, v1);
                     tmem_ld_wait();
-                    const float* wv = w4 + 32 * pp;
+                    const float4* wv4 = reinterpret_cast<const float4*>(w4 + 32 * pp);   // 128-byte aligned
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) partial = fmaf(hact<HIDDEN_ACT>(__uint_as_float(v0[i])), wv[i], partial);
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 w = wv4[j];
+                        partial = fmaf(hact<HIDDEN_ACT>(__uint_as_float(v0[4 * j])), w.x, partial);
+                        partial = fmaf(hact<HIDDEN_ACT>(__uint_as_float(v0[4 * j + 1])), w.y, partial);
+                        partial = fmaf(hact<HIDDEN_ACT>(__uint_as_float(v0[4 * j + 2])), w.z, partial);
+                        partial = fmaf(hact<HIDDEN_ACT>(__uint_as_float(v0[4 * j + 3])), w.w, partial);
+                    }
                     if (two) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) partial = fmaf(hact<HIDDEN_ACT>(__uint_as_float(v1[i])), wv[16 + i], partial);
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 w = wv4[4 + j];
+                            partial = fmaf(hact<HIDDEN_ACT>(__uint_as_float(v1[4 * j])), w.x, partial);
+                            partial = fmaf(hact<HIDDEN_ACT>(__uint_as_float(v1[4 * j + 1])), w.y, partial);
+                            partial = fmaf(hact<HIDDEN_ACT>(__uint_as_float(v1[4 * j + 2])), w.z, partial);
+                            partial = fmaf(hact<HIDDEN_ACT>(__uint_as_float(v1[4 * j + 3])), w.w, partial);
+                        }
                     }
                     if (EMIT) {
                         // last hidden activations a_J (operand of the output layer's weight gradient) and their signs
