@@ -65,6 +65,39 @@ def test_descriptor_validation_and_sizes(lib):
     assert lib.umnn_cc_forward(d0, None, None, None, None, None, None, None, None, None, None, 0, None) == 0
 
 
+def test_precision_modes_sizes_and_auto_resolution(lib, monkeypatch):
+    """Packed-block and workspace sizes of the precision modes (host-only arithmetic, no device needed), and how
+    UMNN_PREC_AUTO resolves: FP16X3 by default, BF16X3 under UMNN_B200_AUTO_TC=bf16x3, FP32 where the tensor-core
+    kernel cannot serve the shape."""
+    def desc(prec, hidden=(200, 200, 200)):
+        return _native.make_desc(_native.LAYOUT_STRIDED_D, 1000, 6, 30, [31] + list(hidden) + [1], _native.ACT_LEAKY_RELU,
+                                 _native.OUT_ELU_PLUS_1, 50, prec)
+    monkeypatch.delenv("UMNN_B200_AUTO_TC", raising=False)
+    bf16 = lib.umnn_packed_params_bytes(desc(_native.PREC_BF16X3))
+    fp16 = lib.umnn_packed_params_bytes(desc(_native.PREC_FP16X3))
+    fp32 = lib.umnn_packed_params_bytes(desc(_native.PREC_FP32))
+    assert bf16 > 0 and fp32 >= 87001 * 4
+    # FP16X3 block = the BF16X3 block (forward + dgrad blobs, rounded up to 256 bytes) followed by the fp16 forward blobs
+    assert fp16 > bf16 and (fp16 - (bf16 + 255) // 256 * 256) * 2 < bf16 * 1.1
+    assert lib.umnn_packed_params_bytes(desc(_native.PREC_AUTO)) == fp16
+    assert lib.umnn_workspace_bytes(desc(_native.PREC_AUTO), 0) == 256       # overflow flag of the guarded re-run
+    assert lib.umnn_workspace_bytes(desc(_native.PREC_FP16X3), 0) == 256
+    assert lib.umnn_workspace_bytes(desc(_native.PREC_BF16X3), 0) == 0
+    assert lib.umnn_workspace_bytes(desc(_native.PREC_FP32), 0) == 0
+    assert lib.umnn_workspace_bytes(desc(_native.PREC_AUTO), 1) >= lib.umnn_workspace_bytes(desc(_native.PREC_BF16X3), 1) > 0
+    monkeypatch.setenv("UMNN_B200_AUTO_TC", "bf16x3")
+    assert lib.umnn_packed_params_bytes(desc(_native.PREC_AUTO)) == bf16
+    assert lib.umnn_workspace_bytes(desc(_native.PREC_AUTO), 0) == 0
+    monkeypatch.delenv("UMNN_B200_AUTO_TC")
+    # one hidden layer: no tensor-core kernel -> AUTO is the FP32 kernel, explicit tensor-core precisions are refused
+    one = desc(_native.PREC_AUTO, hidden=(64,))
+    assert lib.umnn_packed_params_bytes(one) == lib.umnn_packed_params_bytes(desc(_native.PREC_FP32, hidden=(64,)))
+    assert lib.umnn_packed_params_bytes(desc(_native.PREC_FP16X3, hidden=(64,))) == 0
+    assert b"tensor-core" in lib.umnn_last_error()
+    bad = desc(7)
+    assert lib.umnn_packed_params_bytes(bad) == 0 and b"precision" in lib.umnn_last_error()
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_native, "_lib", None)
     monkeypatch.setattr(_native, "LIB_PATH", os.path.join(tmp_path, "nope.so"))

@@ -620,6 +620,27 @@ def test_invert_native_matches_op_by_op_loop(monkeypatch):
     assert np.max(np.abs(x_native.cpu().numpy() - xn[:16])) < 5e-2
 
 
+@pytest.mark.parametrize("iters", [1, 6, 7])
+def test_invert_graph_replay_matches_launch_by_launch(monkeypatch, iters):
+    """One dimension's refinement rounds captured once and replayed per dimension (default) against the same
+    launches issued one by one (UMNN_B200_INVERT_GRAPH=0): identical results, also after a parameter update
+    (the packing launches are part of the captured sequence) and for odd round counts (grid ping-pong)."""
+    model, xn, g = _flow_from_golden(_dev())
+    model.eval()
+    z = torch.from_numpy(g["z"][:16].copy()).to(_dev())
+    for attempt in range(2):
+        with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+            monkeypatch.delenv("UMNN_B200_INVERT_GRAPH", raising=False)
+            x_graph = model.invert(z, iter=iters)
+            monkeypatch.setenv("UMNN_B200_INVERT_GRAPH", "0")
+            x_eager = model.invert(z, iter=iters)
+        assert torch.equal(x_graph, x_eager)
+        with torch.no_grad():
+            for p in model.parameters():
+                if p.requires_grad:
+                    p.mul_(0.97)
+
+
 def test_monotonic_nn_on_cuda():
     from umnn_b200 import MonotonicNN
     torch.manual_seed(0)

@@ -225,31 +225,76 @@ class UMNNMAF(nn.Module):
     def _invert_native(self, z, iter, context, derivative, grid):
         """invert() on the kernel route: per refinement round ONE fused integral launch over the 10*B grid slots
         (contiguous-context layout) and ONE bracket-update launch (umnn_invert_bracket_step) instead of the
-        ~15 torch ops of UMNNMAF.py:213-231.  Same arithmetic, same results."""
+        ~15 torch ops of UMNNMAF.py:213-231.  Same arithmetic, same results.
+
+        The `iter` rounds of one dimension touch only fixed-size buffers, so they are captured ONCE as a CUDA graph
+        and replayed for every dimension (D graph launches instead of D * 2 * iter kernel launches from Python;
+        UMNN_B200_INVERT_GRAPH=0 keeps the launch-by-launch loop).  The conditioner pass between two dimensions
+        stays eager: it depends on the dimensions already inverted."""
         n_grid = grid.shape[0]
         B, D = z.shape
         dev = z.device
         spec = derivative.kernel_spec()
         z = z.contiguous()
         x_inv = torch.zeros(B, D, device=dev)
-        left = torch.full((B, D), -50., device=dev)
-        right = torch.full((B, D), 50., device=dev)
         s = torch.exp(self.scaling.detach()).to(dev).float().contiguous()
+        E = spec.n_ctx
+        # fixed buffers of one dimension's refinement
+        h_j = torch.empty(n_grid * B, E, device=dev)
+        offset = torch.empty(B, device=dev)
+        target = torch.empty(B, device=dev)
+        scale = torch.empty(1, device=dev)
+        left = torch.empty(B, device=dev)
+        right = torch.empty(B, device=dev)
+        x_mid = torch.zeros(B, device=dev)
         x_a = torch.empty(n_grid, B, device=dev)
         x_b = torch.empty(n_grid, B, device=dev)
+        integ = torch.empty(n_grid * B, 1, device=dev)
+
+        def rounds():
+            xa, xb = x_a, x_b
+            kernel.invert_bracket_step(None, None, grid, None, None, None, left, right, xa, None)
+            for _ in range(iter):
+                kernel.cc_forward(spec, None, xa.view(-1, 1), h_j, self.nb_steps, out=integ)
+                kernel.invert_bracket_step(integ.view(n_grid, B), xa, grid, offset, scale, target, left, right, xb, x_mid)
+                xa, xb = xb, xa
+
+        def load(j, h_all):
+            h_j.view(n_grid, B, E).copy_(h_all[:, j::D].unsqueeze(0).expand(n_grid, -1, -1))
+            offset.copy_(h_all[:, j])
+            target.copy_(z[:, j])
+            scale.copy_(s[j:j + 1])
+            left.fill_(-50.)
+            right.fill_(50.)
+
+        use_graph = os.environ.get("UMNN_B200_INVERT_GRAPH", "1") != "0" and D > 1 and \
+            not torch.cuda.is_current_stream_capturing()
+        graph = None
         with torch.no_grad():
             for j in range(self.input_size):
                 if j % 100 == 0:
                     print(j)
                 h_all = self.net.make_embeding(x_inv, context).float()
-                offset = h_all[:, j]
-                h_j = h_all[:, j::D].unsqueeze(0).expand(n_grid, -1, -1).reshape(n_grid * B, -1)
-                kernel.invert_bracket_step(None, None, grid, None, None, None, left[:, j], right[:, j], x_a, None)
-                for _ in range(iter):
-                    integ = kernel.cc_forward(spec, None, x_a.view(-1, 1), h_j, self.nb_steps)[0]
-                    kernel.invert_bracket_step(integ.view(n_grid, B), x_a, grid, offset, s[j:j + 1], z[:, j],
-                                               left[:, j], right[:, j], x_b, x_inv[:, j])
-                    x_a, x_b = x_b, x_a
+                load(j, h_all)
+                if use_graph and graph is None:
+                    # first dimension: run eagerly on a side stream (loads the tables, packs the parameters, sizes the
+                    # allocator pools), then capture; the eager results are the first dimension's
+                    with kernel.repack_every_call():
+                        side = torch.cuda.Stream(device=dev)
+                        side.wait_stream(torch.cuda.current_stream(dev))
+                        with torch.cuda.stream(side):
+                            rounds()
+                        torch.cuda.current_stream(dev).wait_stream(side)
+                        x_inv[:, j] = x_mid
+                        graph = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(graph):
+                            rounds()
+                    continue
+                if graph is not None:
+                    graph.replay()
+                else:
+                    rounds()
+                x_inv[:, j] = x_mid
         return x_inv
 
 
