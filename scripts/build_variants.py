@@ -15,6 +15,8 @@ VARIANTS = {
     "lds_plain": ["-DUMNN_TC_WAIT_STYLE=2", "-DUMNN_TC_WAIT_HINT=0"],
     "gen_plain": ["-DUMNN_TC_SMEM_GENERIC=1", "-DUMNN_TC_WAIT_STYLE=2", "-DUMNN_TC_WAIT_HINT=0"],   # = before this change
     "lds_plain_hint": ["-DUMNN_TC_WAIT_STYLE=2"],
+    "f32x2_on": [],                                                          # = product build
+    "f32x2_off": ["-DUMNN_TC_F32X2=0"],
     "lds_sleep20": ["-DUMNN_TC_WAIT_STYLE=3", "-DUMNN_TC_WAIT_SLEEP_NS=20"],
     "lds_sleep50": ["-DUMNN_TC_WAIT_STYLE=3", "-DUMNN_TC_WAIT_SLEEP_NS=50"],
     "lds_sleep100": ["-DUMNN_TC_WAIT_STYLE=3", "-DUMNN_TC_WAIT_SLEEP_NS=100"],

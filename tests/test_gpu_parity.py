@@ -625,9 +625,12 @@ def test_invert_graph_replay_matches_launch_by_launch(monkeypatch, iters):
     """One dimension's refinement rounds captured once and replayed per dimension (default) against the same
     launches issued one by one (UMNN_B200_INVERT_GRAPH=0): identical results, also after a parameter update
     (the packing launches are part of the captured sequence) and for odd round counts (grid ping-pong)."""
-    model, xn, g = _flow_from_golden(_dev())
+    from umnn_b200 import UMNNMAFFlow
+    torch.manual_seed(0)
+    model = UMNNMAFFlow(nb_flow=1, nb_in=24, hidden_derivative=[50, 50, 50], hidden_embedding=[64, 64], embedding_s=10,
+                        nb_steps=20, solver="CCParallel", device=_dev()).to(_dev())
     model.eval()
-    z = torch.from_numpy(g["z"][:16].copy()).to(_dev())
+    z = torch.randn(16, 24, device=_dev())
     for attempt in range(2):
         with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
             monkeypatch.delenv("UMNN_B200_INVERT_GRAPH", raising=False)

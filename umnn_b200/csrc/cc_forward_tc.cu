@@ -108,14 +108,24 @@ __device__ __forceinline__ void emit16(const PanelRow& R, int col, const uint32_
 // the panels that pass W multiplies with the bf16 dz panels are bf16 in every mode).  TRACK: keep the largest
 // |activation| converted to fp16 (networks whose hidden activation would swallow a NaN: ReLU).
 template <int OPF, bool EMIT, bool TRACK>
-__device__ __forceinline__ void split_pair(float a0, float a1, uint32_t& o_hi, uint32_t& o_lo, uint32_t& p_hi, uint32_t& p_lo,
-                                           float& amax) {
-    split_x2<OPF>(a0, a1, o_hi, o_lo);
+__device__ __forceinline__ void split_pair(float2 a, uint32_t& o_hi, uint32_t& o_lo, uint32_t& p_hi, uint32_t& p_lo, float& amax) {
+    split2<OPF>(a, o_hi, o_lo);
     if constexpr (EMIT) {
         if constexpr (OPF == UMNN_OPF_BF16) { p_hi = o_hi; p_lo = o_lo; }
-        else split_bf16x2(a0, a1, p_hi, p_lo);
+        else split2<UMNN_OPF_BF16>(a, p_hi, p_lo);
     }
-    if constexpr (TRACK) amax = fmaxf(fmaxf(amax, fabsf(a0)), fabsf(a1));
+    if constexpr (TRACK) amax = fmaxf(fmaxf(amax, fabsf(a.x)), fabsf(a.y));
+}
+
+// hidden activation of a pair: the slope multiply is one packed instruction
+template <int HIDDEN_ACT>
+__device__ __forceinline__ float2 hact2(float2 v) {
+    if constexpr (HIDDEN_ACT == UMNN_ACT_LEAKY_RELU) {
+        const float2 t = fmul2(v, make_float2(kLeakySlope, kLeakySlope));
+        return make_float2(fmaxf(v.x, t.x), fmaxf(v.y, t.y));
+    } else {
+        return make_float2(fmaxf(v.x, 0.0f), fmaxf(v.y, 0.0f));
+    }
 }
 
 template <int HIDDEN_ACT, bool EMIT, bool NARROW, int OPF>
@@ -380,16 +390,17 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
             const float4* cv4 = reinterpret_cast<const float4*>(cv);
             const float4* wx4 = reinterpret_cast<const float4*>(wx);
 #pragma unroll
+            const float2 xn2 = make_float2(xn, xn);
+#pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float4 c = cv4[j], w = wx4[j];
-                const float v0 = fmaf(xn, w.x, c.x), v1 = fmaf(xn, w.y, c.y), v2 = fmaf(xn, w.z, c.z), v3 = fmaf(xn, w.w, c.w);
-                split_pair<OPF, EMIT, kTrack>(hact<HIDDEN_ACT>(v0), hact<HIDDEN_ACT>(v1), o[2 * j], o[8 + 2 * j], ob[2 * j],
-                                              ob[8 + 2 * j], amax);
-                split_pair<OPF, EMIT, kTrack>(hact<HIDDEN_ACT>(v2), hact<HIDDEN_ACT>(v3), o[2 * j + 1], o[9 + 2 * j], ob[2 * j + 1],
-                                              ob[9 + 2 * j], amax);
+                const float2 va = ffma2(xn2, make_float2(w.x, w.y), make_float2(c.x, c.y));
+                const float2 vb = ffma2(xn2, make_float2(w.z, w.w), make_float2(c.z, c.w));
+                split_pair<OPF, EMIT, kTrack>(hact2<HIDDEN_ACT>(va), o[2 * j], o[8 + 2 * j], ob[2 * j], ob[8 + 2 * j], amax);
+                split_pair<OPF, EMIT, kTrack>(hact2<HIDDEN_ACT>(vb), o[2 * j + 1], o[9 + 2 * j], ob[2 * j + 1], ob[9 + 2 * j], amax);
                 if (EMIT) {
-                    pre[4 * j] = __float_as_uint(v0); pre[4 * j + 1] = __float_as_uint(v1);
-                    pre[4 * j + 2] = __float_as_uint(v2); pre[4 * j + 3] = __float_as_uint(v3);
+                    pre[4 * j] = __float_as_uint(va.x); pre[4 * j + 1] = __float_as_uint(va.y);
+                    pre[4 * j + 2] = __float_as_uint(vb.x); pre[4 * j + 3] = __float_as_uint(vb.y);
                 }
             }
             tmem_st16(tbase + lane_sel + kColQ + 16u * c16, o);
@@ -447,15 +458,15 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
                     }
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
-                        split_pair<OPF, EMIT, kTrack>(hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i])),
-                                                      hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i + 1])), o[i], o[8 + i], ob[i], ob[8 + i], amax);
+                        split_pair<OPF, EMIT, kTrack>(hact2<HIDDEN_ACT>(make_float2(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]))),
+                                                      o[i], o[8 + i], ob[i], ob[8 + i], amax);
                     tmem_st16(taddr, o);
                     if (EMIT) emit16(prow, 32 * pp, ob);
                     if (two) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
-                            split_pair<OPF, EMIT, kTrack>(hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i])),
-                                                          hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i + 1])), o[i], o[8 + i], ob[i], ob[8 + i], amax);
+                            split_pair<OPF, EMIT, kTrack>(hact2<HIDDEN_ACT>(make_float2(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]))),
+                                                          o[i], o[8 + i], ob[i], ob[8 + i], amax);
                         tmem_st16(taddr + 16, o);
                         if (EMIT) emit16(prow, 32 * pp + 16, ob);
                     }
@@ -483,19 +494,23 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const float4 w = wv4[j];
-                        partial = fmaf(hact<HIDDEN_ACT>(__uint_as_float(v0[4 * j])), w.x, partial);
-                        partial = fmaf(hact<HIDDEN_ACT>(__uint_as_float(v0[4 * j + 1])), w.y, partial);
-                        partial = fmaf(hact<HIDDEN_ACT>(__uint_as_float(v0[4 * j + 2])), w.z, partial);
-                        partial = fmaf(hact<HIDDEN_ACT>(__uint_as_float(v0[4 * j + 3])), w.w, partial);
+                        const float2 a = hact2<HIDDEN_ACT>(make_float2(__uint_as_float(v0[4 * j]), __uint_as_float(v0[4 * j + 1])));
+                        const float2 b = hact2<HIDDEN_ACT>(make_float2(__uint_as_float(v0[4 * j + 2]), __uint_as_float(v0[4 * j + 3])));
+                        partial = fmaf(a.x, w.x, partial);
+                        partial = fmaf(a.y, w.y, partial);
+                        partial = fmaf(b.x, w.z, partial);
+                        partial = fmaf(b.y, w.w, partial);
                     }
                     if (two) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const float4 w = wv4[4 + j];
-                            partial = fmaf(hact<HIDDEN_ACT>(__uint_as_float(v1[4 * j])), w.x, partial);
-                            partial = fmaf(hact<HIDDEN_ACT>(__uint_as_float(v1[4 * j + 1])), w.y, partial);
-                            partial = fmaf(hact<HIDDEN_ACT>(__uint_as_float(v1[4 * j + 2])), w.z, partial);
-                            partial = fmaf(hact<HIDDEN_ACT>(__uint_as_float(v1[4 * j + 3])), w.w, partial);
+                            const float2 a = hact2<HIDDEN_ACT>(make_float2(__uint_as_float(v1[4 * j]), __uint_as_float(v1[4 * j + 1])));
+                            const float2 b = hact2<HIDDEN_ACT>(make_float2(__uint_as_float(v1[4 * j + 2]), __uint_as_float(v1[4 * j + 3])));
+                            partial = fmaf(a.x, w.x, partial);
+                            partial = fmaf(a.y, w.y, partial);
+                            partial = fmaf(b.x, w.z, partial);
+                            partial = fmaf(b.y, w.w, partial);
                         }
                     }
                     if (EMIT) {

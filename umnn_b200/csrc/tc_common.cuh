@@ -344,6 +344,58 @@ __device__ __forceinline__ void split_x2(float even, float odd, uint32_t& hi, ui
 
 constexpr float kFp16Max = 65504.0f;
 
+// ---------------------------------------------------------------------------------------------
+// packed fp32 pairs (sm_100: FFMA2 / FMUL2 / FADD2 -- one issue slot for two IEEE fp32 operations, results identical
+// to the scalar instructions).  UMNN_TC_F32X2=0 compiles the scalar forms instead (experiment switch).
+// ---------------------------------------------------------------------------------------------
+#ifndef UMNN_TC_F32X2
+#define UMNN_TC_F32X2 1
+#endif
+__device__ __forceinline__ unsigned long long f2_bits(float2 v) { return *reinterpret_cast<unsigned long long*>(&v); }
+__device__ __forceinline__ float2 f2_from(unsigned long long b) { return *reinterpret_cast<float2*>(&b); }
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+#if UMNN_TC_F32X2
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+    return f2_from(d);
+#else
+    return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+#if UMNN_TC_F32X2
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return f2_from(d);
+#else
+    return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y));
+#endif
+}
+__device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
+#if UMNN_TC_F32X2
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return f2_from(d);
+#else
+    return make_float2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y));
+#endif
+}
+// hi/lo split of a pair with the residual subtraction as one packed instruction
+template <int OPF>
+__device__ __forceinline__ void split2(float2 a, uint32_t& hi, uint32_t& lo) {
+    float2 h;
+    if constexpr (OPF == UMNN_OPF_BF16) {
+        hi = pack_bf16x2(a.x, a.y);
+        h = make_float2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xFFFF0000u));
+    } else {
+        hi = pack_f16x2(a.x, a.y);
+        h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    }
+    const float2 r = fsub2(a, h);
+    if constexpr (OPF == UMNN_OPF_BF16) lo = pack_bf16x2(r.x, r.y);
+    else lo = pack_f16x2(r.x, r.y);
+}
+
 // sign bits of 16 fp32 bit patterns, element 4k + j -> bit 8j + k (see mask_bitpos in tc_bwd_layout.cuh):
 // three byte permutes gather the top bytes of four values, one shift + mask drops them into place
 __device__ __forceinline__ uint32_t sign_mask16(const uint32_t (&v)[16]) {

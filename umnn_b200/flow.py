@@ -227,10 +227,11 @@ class UMNNMAF(nn.Module):
         (contiguous-context layout) and ONE bracket-update launch (umnn_invert_bracket_step) instead of the
         ~15 torch ops of UMNNMAF.py:213-231.  Same arithmetic, same results.
 
-        The `iter` rounds of one dimension touch only fixed-size buffers, so they are captured ONCE as a CUDA graph
-        and replayed for every dimension (D graph launches instead of D * 2 * iter kernel launches from Python;
-        UMNN_B200_INVERT_GRAPH=0 keeps the launch-by-launch loop).  The conditioner pass between two dimensions
-        stays eager: it depends on the dimensions already inverted."""
+        The `iter` rounds of one dimension touch only fixed-size buffers, so for flows with many dimensions
+        (D >= 16: capturing and instantiating a graph costs about as much as a dozen dimensions) they are captured
+        ONCE per call as a CUDA graph and replayed for every dimension: D graph launches instead of D * 2 * iter
+        kernel launches from Python.  UMNN_B200_INVERT_GRAPH=0 keeps the launch-by-launch loop.  The conditioner
+        pass between two dimensions stays eager: it depends on the dimensions already inverted."""
         n_grid = grid.shape[0]
         B, D = z.shape
         dev = z.device
@@ -267,7 +268,7 @@ class UMNNMAF(nn.Module):
             left.fill_(-50.)
             right.fill_(50.)
 
-        use_graph = os.environ.get("UMNN_B200_INVERT_GRAPH", "1") != "0" and D > 1 and \
+        use_graph = os.environ.get("UMNN_B200_INVERT_GRAPH", "1") != "0" and D >= 16 and \
             not torch.cuda.is_current_stream_capturing()
         graph = None
         with torch.no_grad():
@@ -278,17 +279,17 @@ class UMNNMAF(nn.Module):
                 load(j, h_all)
                 if use_graph and graph is None:
                     # first dimension: run eagerly on a side stream (loads the tables, packs the parameters, sizes the
-                    # allocator pools), then capture; the eager results are the first dimension's
-                    with kernel.repack_every_call():
-                        side = torch.cuda.Stream(device=dev)
-                        side.wait_stream(torch.cuda.current_stream(dev))
-                        with torch.cuda.stream(side):
-                            rounds()
-                        torch.cuda.current_stream(dev).wait_stream(side)
-                        x_inv[:, j] = x_mid
-                        graph = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(graph):
-                            rounds()
+                    # allocator pools), then capture; the eager results are the first dimension's.  The graph lives
+                    # for this call only, so the packed parameters it reads cannot go stale.
+                    side = torch.cuda.Stream(device=dev)
+                    side.wait_stream(torch.cuda.current_stream(dev))
+                    with torch.cuda.stream(side):
+                        rounds()
+                    torch.cuda.current_stream(dev).wait_stream(side)
+                    x_inv[:, j] = x_mid
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        rounds()
                     continue
                 if graph is not None:
                     graph.replay()
