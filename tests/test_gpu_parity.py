@@ -622,9 +622,9 @@ def test_invert_native_matches_op_by_op_loop(monkeypatch):
 
 @pytest.mark.parametrize("iters", [1, 6, 7])
 def test_invert_graph_replay_matches_launch_by_launch(monkeypatch, iters):
-    """One dimension's refinement rounds captured once and replayed per dimension (default) against the same
-    launches issued one by one (UMNN_B200_INVERT_GRAPH=0): identical results, also after a parameter update
-    (the packing launches are part of the captured sequence) and for odd round counts (grid ping-pong)."""
+    """One dimension's refinement rounds captured once and replayed per dimension (UMNN_B200_INVERT_GRAPH=1) against
+    the same launches issued one by one (default): identical results, also after a parameter update and for odd
+    round counts (grid ping-pong)."""
     from umnn_b200 import UMNNMAFFlow
     torch.manual_seed(0)
     model = UMNNMAFFlow(nb_flow=1, nb_in=24, hidden_derivative=[50, 50, 50], hidden_embedding=[64, 64], embedding_s=10,
@@ -633,9 +633,9 @@ def test_invert_graph_replay_matches_launch_by_launch(monkeypatch, iters):
     z = torch.randn(16, 24, device=_dev())
     for attempt in range(2):
         with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
-            monkeypatch.delenv("UMNN_B200_INVERT_GRAPH", raising=False)
+            monkeypatch.setenv("UMNN_B200_INVERT_GRAPH", "1")
             x_graph = model.invert(z, iter=iters)
-            monkeypatch.setenv("UMNN_B200_INVERT_GRAPH", "0")
+            monkeypatch.delenv("UMNN_B200_INVERT_GRAPH")
             x_eager = model.invert(z, iter=iters)
         assert torch.equal(x_graph, x_eager)
         with torch.no_grad():

@@ -227,11 +227,11 @@ class UMNNMAF(nn.Module):
         (contiguous-context layout) and ONE bracket-update launch (umnn_invert_bracket_step) instead of the
         ~15 torch ops of UMNNMAF.py:213-231.  Same arithmetic, same results.
 
-        The `iter` rounds of one dimension touch only fixed-size buffers, so for flows with many dimensions
-        (D >= 16: capturing and instantiating a graph costs about as much as a dozen dimensions) they are captured
-        ONCE per call as a CUDA graph and replayed for every dimension: D graph launches instead of D * 2 * iter
-        kernel launches from Python.  UMNN_B200_INVERT_GRAPH=0 keeps the launch-by-launch loop.  The conditioner
-        pass between two dimensions stays eager: it depends on the dimensions already inverted."""
+        The `iter` rounds of one dimension touch only fixed-size buffers and can be captured once per call as a CUDA
+        graph that is replayed for every dimension (UMNN_B200_INVERT_GRAPH=1, D >= 16).  Off by default: measured on
+        B200 the loop is bound by the conditioner pass and the kernels themselves, not by launches (MNIST shape,
+        D = 784, B = 16: 576 ms with the graph, 565 ms without; BSDS300 shape, D = 63: 56 vs 43 ms -- capture and
+        instantiation cost more than the launches saved)."""
         n_grid = grid.shape[0]
         B, D = z.shape
         dev = z.device
@@ -268,7 +268,7 @@ class UMNNMAF(nn.Module):
             left.fill_(-50.)
             right.fill_(50.)
 
-        use_graph = os.environ.get("UMNN_B200_INVERT_GRAPH", "1") != "0" and D >= 16 and \
+        use_graph = os.environ.get("UMNN_B200_INVERT_GRAPH", "0") == "1" and D >= 16 and \
             not torch.cuda.is_current_stream_capturing()
         graph = None
         with torch.no_grad():
