@@ -230,7 +230,8 @@ def backward_probe(net, cfg, dev, reps=3):
         torch.cuda.synchronize()
         return s.elapsed_time(e) / reps
 
-    for label, prec in (("bf16x3_tensor_core_ms", _native.PREC_BF16X3), ("fp32_ffma_ms", _native.PREC_FP32)):
+    for label, prec in (("tensor_core_default_ms", _native.PREC_AUTO), ("bf16x3_tensor_core_ms", _native.PREC_BF16X3),
+                        ("fp32_ffma_ms", _native.PREC_FP32)):
         if _native.lib().umnn_workspace_bytes(kernel.make_desc(ks, x, Q, prec), 1) > 0:
             res[label] = timed(lambda: kernel.cc_backward(ks, x0, x, h, go, Q, precision=prec))
     res["torch_ops_reference_algorithm_ms"] = timed(lambda: _integrate_grads_chunked(x0, x, net, h, Q, go, False))
@@ -387,9 +388,9 @@ def run_ours(args, cfg, name):
                      "hbm_sanity_gbs": (B * D * slot_bytes) / (ms_per_step * 1e-3) / 1e9,
                      "issued_tensor_tflops": (rows_per_step / world) * issued_per_row / (ms_per_step * 1e-3) / 1e12,
                      "issued_tensor_frac": (rows_per_step / world) * issued_per_row / (ms_per_step * 1e-3) / 1e12 / peak,
-                     "note": "achieved = algorithmic fp32 FLOP (2*sum in*out per row) / time; the BF16x3 scheme issues 3 "
-                             "padded bf16 MMAs per algorithmic MAC on the hidden layers, so frac is capped near 1/3.3; "
-                             "issued_tensor_* counts the bf16 FLOP actually sent to the tensor pipe"},
+                     "note": "achieved = algorithmic fp32 FLOP (2*sum in*out per row) / time; the hi+lo operand split issues 3 "
+                             "padded 16-bit MMAs per algorithmic MAC on the hidden layers, so frac is capped near 1/3.3; "
+                             "issued_tensor_* counts the 16-bit FLOP actually sent to the tensor pipe"},
         "parity": {"integral_max_rel_err_vs_oracle": rel, "log_jac_max_abs_err_vs_oracle": jac_abs, "samples": n_chk},
     }
     if world == 1 and not args.no_cpu:
@@ -411,7 +412,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (debugging only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--precision", default=os.environ.get("UMNN_B200_PRECISION", "auto"), choices=["auto", "fp32", "bf16x3", "fp16x3"],
-                    help="kernel family: auto = BF16x3 tensor cores when the shape fits, else FP32 FFMA")
+                    help="kernel family: auto = tensor cores (fp16x3 split, guarded bf16x3 re-run) when the shape fits, else FP32 FFMA")
     args = ap.parse_args()
     os.environ["UMNN_B200_PRECISION"] = args.precision
     cfg = dict(WORKLOADS[args.workload])
