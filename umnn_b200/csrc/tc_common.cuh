@@ -331,17 +331,6 @@ __device__ __forceinline__ uint32_t pack_f16x2(float even, float odd) {
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(odd), "f"(even));  // first source -> upper half
     return r;
 }
-__device__ __forceinline__ void split_f16x2(float even, float odd, uint32_t& hi, uint32_t& lo) {
-    hi = pack_f16x2(even, odd);
-    const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
-    lo = pack_f16x2(even - h.x, odd - h.y);
-}
-template <int OPF>
-__device__ __forceinline__ void split_x2(float even, float odd, uint32_t& hi, uint32_t& lo) {
-    if constexpr (OPF == UMNN_OPF_BF16) split_bf16x2(even, odd, hi, lo);
-    else split_f16x2(even, odd, hi, lo);
-}
-
 constexpr float kFp16Max = 65504.0f;
 
 // ---------------------------------------------------------------------------------------------
