@@ -20,7 +20,9 @@ dev = torch.device("cuda:0"); net.to(dev).eval()
 t = [torch.from_numpy(a).to(dev) for a in (x0, x, h, g)]
 ks = net.kernel_spec()
 ref = orc.integrate_parallel(spec, flat, x0, x, h, Q)
-for name, prec in (("fp32", _native.PREC_FP32), ("bf16x3", _native.PREC_BF16X3)):
+# [40, 24, 24] takes the narrow (two CTAs per SM) forward shape; the backward's pass F is always the wide shape.
+# fp16x3 adds the guarded bf16 re-runs (no-op launches) of the forward and of the three backward passes.
+for name, prec in (("fp32", _native.PREC_FP32), ("bf16x3", _native.PREC_BF16X3), ("fp16x3", _native.PREC_FP16X3)):
     if which not in ("all", name):
         continue
     out, fx, fx0 = cc_integrate(net, t[0], t[1], t[2], Q, want_fx=True, want_fx0=True, precision=prec)
