@@ -147,7 +147,7 @@ UMNN_API int umnn_cc_forward(const umnn_desc* desc, const float* x0, const float
                     void* workspace, size_t workspace_bytes, void* stream);
 
 /*
- * Diagnostic (needs a CUDA device): which shape of the tensor-core forward kernel serves desc with `extra_rows`
+ * Diagnostic (ctas_per_sm != NULL needs a CUDA device; with NULL only the shape is reported): which shape of the tensor-core forward kernel serves desc with `extra_rows`
  * (0..2) point evaluations per slot -- narrow_shape = 1: two CTAs per SM with 128-column tensor-memory regions
  * (every padded hidden width <= 128), 0: one CTA per SM with 256-column regions -- and how many CTAs of it per SM
  * cudaOccupancyMaxActiveClusters accounts for (informational: for the narrow shape the calculator answers 1 while

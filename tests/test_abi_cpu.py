@@ -98,6 +98,26 @@ def test_precision_modes_sizes_and_auto_resolution(lib, monkeypatch):
     assert lib.umnn_packed_params_bytes(bad) == 0 and b"precision" in lib.umnn_last_error()
 
 
+@pytest.mark.parametrize("hidden,Q,narrow", [([100, 100, 100, 100], 50, 1), ([100, 50, 50, 50, 50], 50, 1), ([126, 126], 50, 1),
+                                             ([127, 127], 50, 0), ([200, 200, 200], 50, 0), ([64, 64, 64], 1000, 1)])
+def test_kernel_shape_selection_is_host_arithmetic(lib, monkeypatch, hidden, Q, narrow):
+    """Which shape of the tensor-core forward serves a descriptor (two CTAs per SM when every padded width fits 128
+    tensor-memory columns and the parameters + context fit half of the shared memory) -- no device involved."""
+    monkeypatch.delenv("UMNN_B200_TC_NARROW", raising=False)
+    d = _native.make_desc(_native.LAYOUT_STRIDED_D, 1000, 6, 30, [31] + hidden + [1], _native.ACT_LEAKY_RELU,
+                          _native.OUT_ELU_PLUS_1, Q, _native.PREC_AUTO)
+    flag = ctypes.c_int32(-1)
+    assert lib.umnn_tc_forward_occupancy(d, 1, ctypes.byref(flag), None) == 0
+    assert flag.value == narrow
+    monkeypatch.setenv("UMNN_B200_TC_NARROW", "0")
+    assert lib.umnn_tc_forward_occupancy(d, 1, ctypes.byref(flag), None) == 0 and flag.value == 0
+    one = _native.make_desc(_native.LAYOUT_STRIDED_D, 10, 6, 30, [31, 64, 1], 1, 0, 50)
+    assert lib.umnn_tc_forward_occupancy(one, 1, ctypes.byref(flag), None) == _native_unsupported
+
+
+_native_unsupported = -4
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_native, "_lib", None)
     monkeypatch.setattr(_native, "LIB_PATH", os.path.join(tmp_path, "nope.so"))

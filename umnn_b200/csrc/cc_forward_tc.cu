@@ -822,6 +822,8 @@ int tc_forward_occupancy(const umnn_desc* d, int extra_rows, int* narrow_out, in
         return UMNN_ERR_UNSUPPORTED;
     }
     const bool narrow = tc_narrow_enabled() && tc_layout_is_narrow(L) && S.total <= kTcNarrowMaxSmem;
+    if (narrow_out) *narrow_out = narrow ? 1 : 0;
+    if (!ctas_per_sm) return 0;          // shape selection only: host arithmetic, no device needed
     const void* kern = narrow ? (const void*)cc_forward_tc_kernel<UMNN_ACT_LEAKY_RELU, false, true, UMNN_OPF_FP16>
                               : (const void*)cc_forward_tc_kernel<UMNN_ACT_LEAKY_RELU, false, false, UMNN_OPF_FP16>;
     UMNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
@@ -842,9 +844,7 @@ int tc_forward_occupancy(const umnn_desc* d, int extra_rows, int* narrow_out, in
     UMNN_CUDA_TRY(cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfg));
     UMNN_CUDA_TRY(cudaGetDevice(&dev));
     UMNN_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    const int n = n_sm > 0 ? (2 * n_clusters) / n_sm : 0;
-    if (narrow_out) *narrow_out = narrow ? 1 : 0;
-    if (ctas_per_sm) *ctas_per_sm = n;
+    *ctas_per_sm = n_sm > 0 ? (2 * n_clusters) / n_sm : 0;
     return 0;
 }
 

@@ -213,7 +213,7 @@ int umnn_tc_forward_occupancy(const umnn_desc* d, int32_t extra_rows, int32_t* n
     int rc = validate_desc(d);
     if (rc) return rc;
     int narrow = 0, n = 0;
-    rc = tc_forward_occupancy(d, extra_rows, &narrow, &n);
+    rc = tc_forward_occupancy(d, extra_rows, &narrow, ctas_per_sm ? &n : nullptr);
     if (rc) return rc;
     if (narrow_shape) *narrow_shape = narrow;
     if (ctas_per_sm) *ctas_per_sm = n;
