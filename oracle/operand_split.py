@@ -42,8 +42,11 @@ def split(a: np.ndarray, fmt: str):
     return hi, lo
 
 
-def mlp_rows_split(spec: orc.MLPSpec, flat: np.ndarray, rows: np.ndarray, fmt: str) -> np.ndarray:
-    """orc.mlp_rows with the hidden-to-hidden layers evaluated through the hi/lo split (three products, exact sums)."""
+def mlp_rows_split(spec: orc.MLPSpec, flat: np.ndarray, rows: np.ndarray, fmt: str, signs: list = None) -> np.ndarray:
+    """orc.mlp_rows with the hidden-to-hidden layers evaluated through the hi/lo split (three products, exact sums).
+
+    ``signs`` (optional list) receives, per hidden layer, the boolean array ``pre-activation < 0`` -- what the
+    backward's re-evaluation records as the derivative mask of the hidden activation."""
     layers = orc.unpack_params(spec, flat)
     a = np.asarray(rows, np.float32)
     n = len(layers)
@@ -61,6 +64,8 @@ def mlp_rows_split(spec: orc.MLPSpec, flat: np.ndarray, rows: np.ndarray, fmt: s
             v = (acc + (b_hi.astype(np.float64) + b_lo.astype(np.float64) + b_3.astype(np.float64))).astype(np.float32)
         else:
             v = (a.astype(np.float64) @ W.T.astype(np.float64) + b.astype(np.float64)).astype(np.float32)
+        if signs is not None and li < n - 1:
+            signs.append(v < 0)
         a = orc._hidden_act(v, spec.hidden_act) if li < n - 1 else orc._out_act(v, spec.out_act)
     return a.reshape(-1)
 
