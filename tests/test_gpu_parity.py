@@ -149,7 +149,7 @@ def test_narrow_shape_really_overlaps_two_tiles_per_sm():
         else:
             os.environ["UMNN_B200_TC_NARROW"] = prev
     assert rel_err(res["1"][1], res["0"][1]) < 2e-6
-    assert res["0"][0] / res["1"][0] > 1.15, (res["1"][0], res["0"][0])
+    assert res["0"][0] / res["1"][0] > 1.08, (res["1"][0], res["0"][0])       # 0.7 .. 1.0 if only one CTA fits per SM
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
