@@ -57,16 +57,18 @@ enum { UMNN_OUT_ELU_PLUS_1 = 0, UMNN_OUT_SIGMOID = 1 };        /* UMNNMAF.py:11-
  * Arithmetic of the hidden-to-hidden layers (layer 1, the output layer, activations and the quadrature sum are
  * fp32 on CUDA cores in every mode):
  *   UMNN_PREC_FP32    FFMA kernel, any shape within UMNN_MAX_*.
- *   UMNN_PREC_BF16X3  tcgen05 tensor cores, operands split into bf16 hi + lo (3 MMAs per product, fp32 accumulate,
- *                     ~17 bits per operand, fp32 exponent range).
- *   UMNN_PREC_FP16X3  same scheme with fp16 hi + lo operands (22 bits per operand: integrals within 3e-6 of the
- *                     fp32 reference where BF16X3 reaches 2e-5).  fp16 overflows above 65504: the kernel raises a
- *                     device flag (in the forward workspace) when an activation leaves that range and a second
- *                     launch of the BF16X3 kernel -- a no-op while the flag is clear -- recomputes the call, so the
- *                     result is never worse than BF16X3 and the host never has to look.
- *   UMNN_PREC_AUTO    FP16X3 (or BF16X3 if the environment variable UMNN_B200_AUTO_TC=bf16x3 is set) where the
- *                     tensor-core kernel serves the shape (>= 2 hidden layers, widths <= 254, parameters within
- *                     shared memory), else FP32.
+ *   UMNN_PREC_FP16X3  tcgen05 tensor cores, operands split into fp16 hi + lo (3 MMAs per product, fp32 accumulate,
+ *                     22 bits per operand: integrals within 3e-6 of the fp32 reference on every tested network).
+ *                     fp16 overflows above 65504: the kernel raises a device flag (head of the workspace) when an
+ *                     activation leaves that range and a second launch -- the FP32 kernel, a no-op while the flag is
+ *                     clear -- recomputes the call, so the rare overflow case gets the parity anchor's arithmetic and
+ *                     the host never has to look.
+ *   UMNN_PREC_AUTO    FP16X3 where the tensor-core kernel serves the shape (>= 2 hidden layers, widths <= 254,
+ *                     parameters within shared memory), else FP32.  This is what the product uses.
+ *   UMNN_PREC_BF16X3  DIAGNOSTIC ONLY -- the same scheme with bf16 hi + lo operands (~17 bits per operand, fp32
+ *                     exponent range, no guard needed).  It meets the 1e-5 integral bar on default-initialised
+ *                     networks (4e-7..8e-7) but NOT on trained-scale weights (1e-5..2.2e-5 measured): it is never
+ *                     selected by AUTO and exists for A/B measurements of the operand formats.
  */
 enum { UMNN_PREC_FP32 = 0, UMNN_PREC_BF16X3 = 1, UMNN_PREC_AUTO = 2, UMNN_PREC_FP16X3 = 3 };
 
@@ -115,11 +117,18 @@ UMNN_API int64_t umnn_param_count(const umnn_desc* desc);
  * `flat_params` is the device vector described above.  Re-pack after every parameter update.
  */
 UMNN_API size_t umnn_packed_params_bytes(const umnn_desc* desc);
+/*
+ * Identifier of the packed block's internal layout for desc (resolved precision, offsets of its parts): two
+ * descriptors with the same id can share one packed block; 0 = invalid desc.  The layout depends on nb_steps
+ * (through the shared-memory fit that UMNN_PREC_AUTO resolves with), so a cache of packed blocks must key on this.
+ */
+UMNN_API uint64_t umnn_packed_layout_id(const umnn_desc* desc);
 UMNN_API int umnn_pack_params(const umnn_desc* desc, const float* flat_params, void* params_packed, void* stream);
 
 /*
  * Scratch the forward (for_backward = 0) / backward (1) entry points need for desc (0 is possible).  The forward
- * needs 256 bytes for UMNN_PREC_FP16X3 (the overflow flag of the guarded re-run) and nothing otherwise.
+ * needs 256 bytes for UMNN_PREC_FP16X3 (the overflow flag of the guarded re-run) and nothing otherwise; the FP16X3
+ * backward's workspace starts with the same 256-byte flag block.
  */
 UMNN_API size_t umnn_workspace_bytes(const umnn_desc* desc, int32_t for_backward);
 
@@ -171,7 +180,8 @@ UMNN_API int umnn_tc_forward_occupancy(const umnn_desc* desc, int32_t extra_rows
  * desc.precision selects the path (and must be the precision params_packed was packed with):
  * UMNN_PREC_BF16X3 / FP16X3 / AUTO = three tensor-core passes per chunk of rows (forward re-evaluation with operand
  * emission, dgrad with transposed weights, split-K weight-gradient GEMM; FP16X3 re-evaluates with fp16 operands
- * and repeats the passes with bf16 operands if an activation left the fp16 range), UMNN_PREC_FP32 = fused FFMA
+ * and, if an activation left the fp16 range, repeats the whole backward with the FP32 kernels -- or with bf16
+ * operands for the few shapes the FP32 backward cannot hold in shared memory), UMNN_PREC_FP32 = fused FFMA
  * kernel + FFMA split-K GEMM.  workspace must hold umnn_workspace_bytes(desc, 1) bytes (operand panels of one chunk;
  * the batch is processed in chunks of whole slots).  A shape the tensor-core backward cannot serve returns
  * UMNN_ERR_UNSUPPORTED (retry with UMNN_PREC_FP32).  Deterministic (fixed reduction order).

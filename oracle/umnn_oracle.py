@@ -304,6 +304,49 @@ def integral_backward(spec: MLPSpec, flat: np.ndarray, x0: np.ndarray, x: np.nda
     return d_x0, d_x, d_flat, d_h
 
 
+def kink_margins(spec: MLPSpec, flat: np.ndarray, x0: np.ndarray, x: np.ndarray, h: np.ndarray, Q: int,
+                 layout: str = "strided", chunk: int = 64) -> np.ndarray:
+    """Per slot, the smallest RELATIVE distance of any hidden pre-activation from its kink over every row the
+    backward evaluates (the Q+1 nodes, x and x0):   min |v| / (sum_k |W_k a_k| + |b|).
+
+    Diagnostic of the gradient tests, not a restatement of a reference function: LeakyReLU/ReLU derivatives are
+    discontinuous at 0, so an implementation whose pre-activations differ from another's by a relative rounding
+    error eps may evaluate a unit on the other side of its kink wherever this margin is below eps -- the
+    reference's own fp32 vs fp64 gradients differ by 1.2e-4 for that reason.  Slots whose margin
+    is below an implementation's rounding level are "kink-ambiguous": their d_h / d_x may legitimately differ by
+    one unit's contribution.  float64 arithmetic.  Returns [B, Dx].
+    """
+    f64 = lambda a: np.asarray(a, dtype=np.float64)
+    x0, x, h, flat = f64(x0), f64(x), f64(h), f64(flat)
+    _, t = cc_nodes_weights(Q)
+    t = t.astype(np.float64)
+    B, Dx = x.shape
+    layers = unpack_params(spec, flat)
+    out = np.empty((B, Dx))
+    for s in range(0, B, chunk):
+        sl = slice(s, min(B, s + chunk))
+        x0c, xc, hc = x0[sl], x[sl], h[sl]
+        n = xc.shape[0]
+        xT = _limits(x0c.astype(np.float32), xc.astype(np.float32), Q).astype(np.float64)
+        nodes = x0c[:, None, :] + (xT - x0c)[:, None, :] * (t[None, :, None] + 1.0) / 2.0          # [n, Q+1, Dx]
+        pts = np.concatenate([nodes, xc[:, None, :], x0c[:, None, :]], axis=1)                     # [n, Q+3, Dx]
+        R = pts.shape[1]
+        h_rep = np.broadcast_to(hc[:, None, :], (n, R, hc.shape[1])).reshape(n * R, -1)
+        if layout == "strided":
+            rows = slot_inputs_strided(pts.reshape(n * R, Dx), h_rep)                              # [(n*R)*Dx, 1+E]
+        else:
+            rows = np.concatenate([pts.reshape(n * R, 1), h_rep], axis=1)
+        a = rows
+        margin = np.full(a.shape[0], np.inf)
+        for (W, b) in layers[:-1]:
+            v = a @ W.T + b
+            scale = np.abs(a) @ np.abs(W).T + np.abs(b)
+            margin = np.minimum(margin, np.min(np.abs(v) / np.maximum(scale, 1e-300), axis=1))
+            a = _hidden_act(v, spec.hidden_act)
+        out[sl] = margin.reshape(n, R, Dx).min(axis=1)
+    return out
+
+
 # ----------------------------------------------------------------------------
 # MADE conditioner (produces h); only what the flow path needs
 # ----------------------------------------------------------------------------

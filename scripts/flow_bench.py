@@ -1,6 +1,6 @@
 """Flow-level timings: UMNNMAFFlow.compute_ll forward, a full training step (forward + backward +
 Adam) and invert, for flows shaped like the reference's drivers, on the kernel route and -- where memory allows --
-with UMNN_B200_ROUTE=torch (the reference's algorithm as torch-CUDA ops in the same process).
+inside `umnn_b200.torch_route()` (the reference's algorithm as torch-CUDA ops in the same process).
 
   python scripts/flow_bench.py [toy|power|bsds|mnist ...] [--no-torch]
 """
@@ -41,8 +41,13 @@ def build(cfg, blocks=None):
 
 
 def bench_route(name, cfg, route, B, do_invert):
-    os.environ["UMNN_B200_ROUTE"] = "torch" if route == "torch" else ""
+    from umnn_b200 import torch_route
     os.environ["UMNN_B200_INVERT"] = "torch" if route == "torch" else ""
+    with (torch_route() if route == "torch" else contextlib.nullcontext()):
+        _bench_route(name, cfg, route, B, do_invert)
+
+
+def _bench_route(name, cfg, route, B, do_invert):
     dev = torch.device("cuda:0")
     out = {"flow": name, "route": route, "B": B, "D": cfg["D"], "Q": cfg["Q"], "blocks": cfg["blocks"]}
     model = build(cfg)

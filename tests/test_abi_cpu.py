@@ -65,30 +65,26 @@ def test_descriptor_validation_and_sizes(lib):
     assert lib.umnn_cc_forward(d0, None, None, None, None, None, None, None, None, None, None, 0, None) == 0
 
 
-def test_precision_modes_sizes_and_auto_resolution(lib, monkeypatch):
+def test_precision_modes_sizes_and_auto_resolution(lib):
     """Packed-block and workspace sizes of the precision modes (host-only arithmetic, no device needed), and how
-    UMNN_PREC_AUTO resolves: FP16X3 by default, BF16X3 under UMNN_B200_AUTO_TC=bf16x3, FP32 where the tensor-core
-    kernel cannot serve the shape."""
+    UMNN_PREC_AUTO resolves: FP16X3 where the tensor-core kernel serves the shape, FP32 elsewhere."""
     def desc(prec, hidden=(200, 200, 200)):
         return _native.make_desc(_native.LAYOUT_STRIDED_D, 1000, 6, 30, [31] + list(hidden) + [1], _native.ACT_LEAKY_RELU,
                                  _native.OUT_ELU_PLUS_1, 50, prec)
-    monkeypatch.delenv("UMNN_B200_AUTO_TC", raising=False)
     bf16 = lib.umnn_packed_params_bytes(desc(_native.PREC_BF16X3))
     fp16 = lib.umnn_packed_params_bytes(desc(_native.PREC_FP16X3))
     fp32 = lib.umnn_packed_params_bytes(desc(_native.PREC_FP32))
     assert bf16 > 0 and fp32 >= 87001 * 4
-    # FP16X3 block = the BF16X3 block (forward + dgrad blobs, rounded up to 256 bytes) followed by the fp16 forward blobs
-    assert fp16 > bf16 and (fp16 - (bf16 + 255) // 256 * 256) * 2 < bf16 * 1.1
+    # FP16X3 block = the BF16X3 block (forward + dgrad blobs, rounded up to 256 bytes), the fp16 forward blobs, and
+    # the FP32 block of the guarded re-run
+    assert fp16 > bf16 + fp32 and (fp16 - fp32 - (bf16 + 255) // 256 * 256) * 2 < bf16 * 1.1
     assert lib.umnn_packed_params_bytes(desc(_native.PREC_AUTO)) == fp16
     assert lib.umnn_workspace_bytes(desc(_native.PREC_AUTO), 0) == 256       # overflow flag of the guarded re-run
     assert lib.umnn_workspace_bytes(desc(_native.PREC_FP16X3), 0) == 256
     assert lib.umnn_workspace_bytes(desc(_native.PREC_BF16X3), 0) == 0
     assert lib.umnn_workspace_bytes(desc(_native.PREC_FP32), 0) == 0
-    assert lib.umnn_workspace_bytes(desc(_native.PREC_AUTO), 1) >= lib.umnn_workspace_bytes(desc(_native.PREC_BF16X3), 1) > 0
-    monkeypatch.setenv("UMNN_B200_AUTO_TC", "bf16x3")
-    assert lib.umnn_packed_params_bytes(desc(_native.PREC_AUTO)) == bf16
-    assert lib.umnn_workspace_bytes(desc(_native.PREC_AUTO), 0) == 0
-    monkeypatch.delenv("UMNN_B200_AUTO_TC")
+    # FP16X3 backward: 256-byte flag block + the tensor-core panels (which the FP32 re-run borrows)
+    assert lib.umnn_workspace_bytes(desc(_native.PREC_AUTO), 1) >= 256 + lib.umnn_workspace_bytes(desc(_native.PREC_BF16X3), 1) > 256
     # one hidden layer: no tensor-core kernel -> AUTO is the FP32 kernel, explicit tensor-core precisions are refused
     one = desc(_native.PREC_AUTO, hidden=(64,))
     assert lib.umnn_packed_params_bytes(one) == lib.umnn_packed_params_bytes(desc(_native.PREC_FP32, hidden=(64,)))
@@ -96,6 +92,31 @@ def test_precision_modes_sizes_and_auto_resolution(lib, monkeypatch):
     assert b"tensor-core" in lib.umnn_last_error()
     bad = desc(7)
     assert lib.umnn_packed_params_bytes(bad) == 0 and b"precision" in lib.umnn_last_error()
+
+
+def test_packed_layout_id_follows_the_nb_steps_threshold(lib):
+    """UMNN_PREC_AUTO resolves through the shared-memory fit, which depends on nb_steps: [200]^3 is the FP32 layout
+    for small Q and the tensor-core layout for larger Q.  The layout id (the key of the Python-side packed-parameter
+    cache) must differ exactly where the packed block differs, so an eval-mode network whose Q changes across the
+    threshold can never be launched on a block in the other format."""
+    def desc(Q, prec=_native.PREC_AUTO):
+        return _native.make_desc(_native.LAYOUT_STRIDED_D, 1000, 6, 30, [31, 200, 200, 200, 1], _native.ACT_LEAKY_RELU,
+                                 _native.OUT_ELU_PLUS_1, Q, prec)
+    sizes = {Q: lib.umnn_packed_params_bytes(desc(Q)) for Q in (5, 10, 20, 50, 100, 400)}
+    ids = {Q: lib.umnn_packed_layout_id(desc(Q)) for Q in sizes}
+    assert all(v != 0 for v in ids.values())
+    fp32_bytes = lib.umnn_packed_params_bytes(desc(5, _native.PREC_FP32))
+    assert sizes[5] == fp32_bytes and sizes[100] > fp32_bytes           # the threshold exists for this shape
+    for a in sizes:
+        for b in sizes:
+            if sizes[a] != sizes[b]:
+                assert ids[a] != ids[b]
+    assert ids[50] == ids[100]                                          # same layout -> the block is shared
+    assert ids[5] == lib.umnn_packed_layout_id(desc(5, _native.PREC_FP32))
+    assert lib.umnn_packed_layout_id(desc(50, _native.PREC_BF16X3)) != ids[50]
+    bad = desc(50)
+    bad.nb_steps = 0
+    assert lib.umnn_packed_layout_id(bad) == 0
 
 
 @pytest.mark.parametrize("hidden,Q,narrow", [([100, 100, 100, 100], 50, 1), ([100, 50, 50, 50, 50], 50, 1), ([126, 126], 50, 1),

@@ -1,10 +1,12 @@
 """GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle and the golden
 vectors recorded from the reference.  Run on the B200 box with `pytest -m gpu`.
 
-Tolerances (float32 path): integral max rel-err <= 1e-5 (north star; the FP32 kernel is expected
-near 5e-7, the noise floor between two fp32 summation orders); point evaluations within
-1e-5 relative + two ELU+1 quanta (2^-23) absolute; gradients <= 1e-3 rel-to-max (fp32 vs
-fp64 reference gradients already differ by 1.2e-4 because of LeakyReLU kink flips).
+Tolerances: integral max rel-err <= 1e-5 (north star) for EVERY precision the product selects, on every network
+(the FP32 kernel is expected near 5e-7, the noise floor between two fp32 summation orders; FP16x3 measures
+3e-7..2.5e-6); point evaluations within 1e-5 relative + two ELU+1 quanta (2^-23) absolute.  Gradients use the
+flip-aware metric of conftest.py: against the float64 oracle, every slot whose hidden pre-activations stay clear of
+their kinks must agree to 1e-4 of the largest entry, slots that deviate must be explained by a near-kink unit and are
+counted, and everything together is held to 2e-3 normwise (d_params additionally to 5e-3 of its largest entry).
 """
 import contextlib
 import io
@@ -14,48 +16,24 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN_CASES, GOLDEN_DIR, load_golden_case, rel_err, rel_to_max
+from conftest import (GOLDEN_CASES, GOLDEN_DIR, assert_slot_grad_ok, assert_sum_grad_ok, dh_to_slots, load_golden_case,
+                      norm_err, rel_err, rel_to_max)
 from oracle import c_binding, umnn_oracle as orc
 
 pytestmark = pytest.mark.gpu
 
 INTEGRAL_TOL = 1e-5
-GRAD_TOL = 1e-3
-# BF16x3 tensor-core path: operands carry ~17.5 bits (hi + lo bf16), i.e. ~90x the fp32 rounding unit.
-# Default-initialised networks (the benchmark configurations) stay below 1e-6 (measured 4e-7..8e-7, inside
-# the north star's 1e-5); the "trained-like" stress networks (weights x1.5..x2.5, ELU saturating, large
-# cancellation) measure 1e-5..2e-5, so those cases are held to 5e-5 in BF16x3 mode and to 1e-5 in FP32 mode.
-TC_STRESS_TOL = 5e-5
 
-# "auto" resolves to the FP16x3 tensor-core split (fp16 hi + lo operands, 22 bits, guarded bf16 re-run) wherever the
-# tensor-core kernel serves the shape, else to the FP32 kernel; "auto-bf16" makes the same choice with the BF16x3 split
-# (UMNN_B200_AUTO_TC=bf16x3).  Explicit "fp16x3" / "bf16x3" raise on shapes the tensor-core kernel cannot serve.
-PRECISIONS = ["fp32", "auto", "auto-bf16"]
+# "auto" resolves to the FP16x3 tensor-core split (fp16 hi + lo operands, 22 bits, guarded FP32 re-run) wherever the
+# tensor-core kernel serves the shape, else to the FP32 kernel.  Explicit "fp16x3" / "bf16x3" raise on shapes the
+# tensor-core kernel cannot serve; "bf16x3" is a diagnostic precision (include/umnn_b200.h) that AUTO never selects.
+PRECISIONS = ["fp32", "auto"]
 
 
 def _prec(name):
     from umnn_b200 import _native
     return {"fp32": _native.PREC_FP32, "bf16x3": _native.PREC_BF16X3, "auto": _native.PREC_AUTO,
-            "auto-bf16": _native.PREC_AUTO, "fp16x3": _native.PREC_FP16X3}[name]
-
-
-@contextlib.contextmanager
-def _auto_split(precision):
-    """The library reads UMNN_B200_AUTO_TC on every call: pin it for the duration of one kernel call."""
-    prev = os.environ.get("UMNN_B200_AUTO_TC")
-    os.environ["UMNN_B200_AUTO_TC"] = "bf16x3" if precision == "auto-bf16" else "fp16x3"
-    try:
-        yield
-    finally:
-        if prev is None:
-            os.environ.pop("UMNN_B200_AUTO_TC", None)
-        else:
-            os.environ["UMNN_B200_AUTO_TC"] = prev
-
-
-def _tol(precision, gain=1.0):
-    # FP16x3 holds the north-star tolerance on the stress networks too (measured 1.3e-6..2.5e-6)
-    return TC_STRESS_TOL if (precision in ("bf16x3", "auto-bf16") and gain != 1.0) else INTEGRAL_TOL
+            "fp16x3": _native.PREC_FP16X3}[name]
 
 
 def _dev():
@@ -86,11 +64,9 @@ def _run_kernel(spec, flat, x0, x, h, Q, layout, want_f=True, x0_none=False, pre
     from umnn_b200 import cc_integrate
     net = _net_for(spec, flat, layout, x.shape[1])
     d = _dev()
-    with _auto_split(precision):
-        out, fx, fx0 = cc_integrate(net, None if x0_none else torch.from_numpy(x0).to(d), torch.from_numpy(x).to(d),
-                                    torch.from_numpy(h).to(d), Q, want_fx=want_f, want_fx0=want_f,
-                                    precision=_prec(precision))
-        torch.cuda.synchronize()
+    out, fx, fx0 = cc_integrate(net, None if x0_none else torch.from_numpy(x0).to(d), torch.from_numpy(x).to(d),
+                                torch.from_numpy(h).to(d), Q, want_fx=want_f, want_fx0=want_f, precision=_prec(precision))
+    torch.cuda.synchronize()
     return out.cpu().numpy(), None if fx is None else fx.cpu().numpy(), None if fx0 is None else fx0.cpu().numpy()
 
 
@@ -156,7 +132,7 @@ def test_narrow_shape_really_overlaps_two_tiles_per_sm():
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_forward_matches_golden_and_oracle(name, precision):
     spec, flat, inp, g = load_golden_case(name)
-    tol = _tol(precision, float(g["meta_gain"]))
+    tol = INTEGRAL_TOL
     out, fx, fx0 = _run_kernel(spec, flat, inp["x0"], inp["x"], inp["h"], inp["Q"], inp["layout"], precision=precision)
     assert rel_err(out, g["par_integral"]) < tol
     assert rel_err(out, g["fp64_integral"].astype(np.float32)) < tol
@@ -182,13 +158,21 @@ def test_autograd_function_on_cuda_matches_golden(name, fn_name):
     h = torch.from_numpy(inp["h"]).to(d).requires_grad_(True)
     z = fn.apply(x0, x, net, torch.cat([p.view(-1) for p in net.parameters()]), h, inp["Q"])
     z.backward(torch.from_numpy(inp["grad_out"]).to(d))
-    tol = _tol("auto", float(g["meta_gain"]))
+    tol = INTEGRAL_TOL
     assert rel_err(z.detach().cpu().numpy(), g["par_integral"]) < tol
     assert rel_to_max(x.grad.cpu().numpy(), g["par_dx"]) < tol
     assert rel_to_max(x0.grad.cpu().numpy(), g["par_dx0"]) < tol
-    assert _grad_ok(h.grad.cpu().numpy(), g["par_dh"], "auto")
+    # gradients against the float64 oracle with the flip-aware metric, and the reference's own fp32 vectors within
+    # the plain bounds (the reference flips kinks against float64 too)
+    B, Dx, layout = inp["B"], inp["Dx"], inp["layout"]
+    margins = orc.kink_margins(spec, flat, inp["x0"], inp["x"], inp["h"], inp["Q"], layout)
+    _, _, r_flat, r_h = _oracle_backward_with_jac(spec, flat, inp, None)
+    assert_slot_grad_ok(dh_to_slots(h.grad.cpu().numpy(), B, Dx, layout), dh_to_slots(r_h, B, Dx, layout), margins, "auto",
+                        (B, Dx, -1), what=f"{name} d_h")
     dflat = torch.cat([p.grad.view(-1) for p in net.parameters()]).cpu().numpy()
-    assert _grad_ok(dflat[::int(g["meta_dflat_stride"])], g["par_dflat"], "auto")
+    assert_sum_grad_ok(dflat, r_flat, what=f"{name} d_params")
+    assert_sum_grad_ok(dflat[::int(g["meta_dflat_stride"])], g["par_dflat"], what=f"{name} d_params vs reference")
+    assert norm_err(h.grad.cpu().numpy(), g["par_dh"]) < 2e-3
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -200,7 +184,7 @@ def test_node_count_edges(Q, precision):
     x0, x, h, _ = orc.synth_inputs(13, 5, 15, Q + 1, x0_zero=False)
     out, fx, fx0 = _run_kernel(spec, flat, x0, x, h, Q, "strided", precision=precision)
     ref, rfx, rfx0 = c_binding.cc_forward(spec, flat, x0, x, h, Q)
-    tol = _tol(precision, 2.0)
+    tol = INTEGRAL_TOL
     assert rel_err(out, ref) < tol
     assert _point_ok(fx, rfx, tol) and _point_ok(fx0, rfx0, tol)
 
@@ -216,7 +200,7 @@ def test_network_shapes_strided(hidden, acts, precision):
     x0, x, h, _ = orc.synth_inputs(B, D, E * D, 3, x0_zero=False)
     out, fx, fx0 = _run_kernel(spec, flat, x0, x, h, Q, "strided", precision=precision)
     ref, rfx, rfx0 = c_binding.cc_forward(spec, flat, x0, x, h, Q)
-    tol = _tol(precision, 1.7)
+    tol = INTEGRAL_TOL
     assert rel_err(out, ref) < tol
     assert _point_ok(fx, rfx, tol) and _point_ok(fx0, rfx0, tol)
 
@@ -229,7 +213,7 @@ def test_contiguous_layout_and_context_sizes(E, precision):
     x0, x, h, _ = orc.synth_inputs(41, 1, E, 5, x0_zero=False)
     out, fx, fx0 = _run_kernel(spec, flat, x0, x, h, 25, "contig", precision=precision)
     ref, rfx, rfx0 = c_binding.cc_forward(spec, flat, x0, x, h, 25, layout="contig")
-    tol = _tol(precision, 1.5)
+    tol = INTEGRAL_TOL
     assert rel_err(out, ref) < tol
     assert _point_ok(fx, rfx, tol) and _point_ok(fx0, rfx0, tol)
 
@@ -255,9 +239,6 @@ def test_degenerate_limits_and_antisymmetry():
     fwd, _, _ = _run_kernel(spec, flat, x0, x, h, 50, "strided", want_f=False)
     bwd, _, _ = _run_kernel(spec, flat, x, x0, h, 50, "strided", want_f=False)
     assert rel_err(-bwd, fwd, floor=1e-4) < 1e-5
-    fwd, _, _ = _run_kernel(spec, flat, x0, x, h, 50, "strided", want_f=False, precision="auto-bf16")
-    bwd, _, _ = _run_kernel(spec, flat, x, x0, h, 50, "strided", want_f=False, precision="auto-bf16")
-    assert rel_err(-bwd, fwd, floor=1e-4) < TC_STRESS_TOL
     fwd, _, _ = _run_kernel(spec, flat, x0, x, h, 50, "strided", want_f=False, precision="fp32")
     bwd, _, _ = _run_kernel(spec, flat, x, x0, h, 50, "strided", want_f=False, precision="fp32")
     assert rel_err(-bwd, fwd, floor=1e-4) < 1e-5
@@ -278,9 +259,11 @@ def test_deterministic_and_batch_invariant(precision):
 @pytest.mark.parametrize("layout", ["strided", "contig"])
 def test_fp16x3_overflow_is_caught_by_the_guarded_rerun(layout):
     """Activations beyond the fp16 range (|a| > 65504) would become inf in the fp16 operands; the kernel tracks the
-    largest value it converts and raises a device flag, and the second (bf16) launch -- a no-op otherwise -- recomputes
-    the call: the result is bit-identical to BF16X3 and finite.  The ReLU network (contig) would swallow a NaN in
-    max(v, 0), which is why the flag does not rely on NaN propagation."""
+    largest value it converts (ReLU) or sees the NaN that the inf/-inf pair produces downstream (LeakyReLU) and raises
+    a device flag, and the second launch -- the FP32 kernel, a no-op otherwise -- recomputes the call: the result is
+    bit-identical to UMNN_PREC_FP32, i.e. the rare overflow case gets the parity anchor's arithmetic and meets the
+    same 1e-5 bar as everything else.  The ReLU network (contig) would swallow a NaN in max(v, 0), which is why the
+    flag does not rely on NaN propagation there."""
     if layout == "strided":
         spec = orc.MLPSpec((31, 200, 200, 200, 1))
         x0, x, h, _ = orc.synth_inputs(64, 6, 180, 2, x0_zero=True)
@@ -289,24 +272,27 @@ def test_fp16x3_overflow_is_caught_by_the_guarded_rerun(layout):
         x0, x, h, _ = orc.synth_inputs(300, 1, 2, 2, x0_zero=True)
     flat = orc.synth_params(spec, 0, 1.0)
     big = (x * 3.0e6).astype(np.float32)
-    a, fa, _ = _run_kernel(spec, flat, x0, big, h, 50, layout, precision="fp16x3")
-    b, fb, _ = _run_kernel(spec, flat, x0, big, h, 50, layout, precision="bf16x3")
-    assert np.all(np.isfinite(a)) and np.all(np.isfinite(fa))
-    np.testing.assert_array_equal(a, b)
-    np.testing.assert_array_equal(fa, fb)
+    for prec in ("fp16x3", "auto"):
+        a, fa, _ = _run_kernel(spec, flat, x0, big, h, 50, layout, precision=prec)
+        b, fb, _ = _run_kernel(spec, flat, x0, big, h, 50, layout, precision="fp32")
+        assert np.all(np.isfinite(a)) and np.all(np.isfinite(fa))
+        np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(fa, fb)
     ref, _, _ = c_binding.cc_forward(spec, flat, x0, big, h, 50, layout)
-    assert rel_err(a, ref) < 1e-4
-    # in range: the re-run stays a no-op and the fp16 result stands (it differs from bf16 in the last bits)
+    assert rel_err(a, ref) < INTEGRAL_TOL
+    # in range: the re-run stays a no-op and the fp16 result stands (it differs from fp32 in the last bits)
     c, _, _ = _run_kernel(spec, flat, x0, x, h, 50, layout, precision="fp16x3")
-    d, _, _ = _run_kernel(spec, flat, x0, x, h, 50, layout, precision="bf16x3")
+    d, _, _ = _run_kernel(spec, flat, x0, x, h, 50, layout, precision="fp32")
     assert not np.array_equal(c, d)
     ref, _, _ = c_binding.cc_forward(spec, flat, x0, x, h, 50, layout)
     assert rel_err(c, ref) < 2e-6
 
 
-def test_fp16x3_backward_overflow_falls_back_to_bf16():
-    """Same guard in the backward: an overflowing re-evaluation makes the second (bf16) sequence of passes run, so the
-    gradients equal the BF16X3 backward bit for bit; in range the two differ."""
+def test_fp16x3_backward_overflow_reruns_in_fp32():
+    """Same guard in the backward: an overflowing re-evaluation makes the second sequence of launches -- the FP32
+    backward, gated on the device flag -- recompute every gradient; in range they stay no-ops.  The per-slot outputs
+    then equal the FP32 backward's up to the order in which a slot that straddles two tiles is summed; d_params is a
+    sum over differently sized chunks (the re-run borrows the tensor-core workspace), so it agrees to rounding."""
     from umnn_b200 import kernel
     spec = orc.MLPSpec((31, 200, 200, 200, 1))
     flat = orc.synth_params(spec, 0, 1.0)
@@ -314,17 +300,39 @@ def test_fp16x3_backward_overflow_falls_back_to_bf16():
     net = _net_for(spec, flat, "strided", 6)
     ks = net.kernel_spec()
     d = _dev()
-    for scale, same in ((3.0e6, True), (1.0, False)):
+    for scale, overflow in ((3.0e6, True), (1.0, False)):
         xb = x.copy()
         xb[-100:] *= scale                                             # only the second chunk leaves the fp16 range
         xs = torch.from_numpy(xb.astype(np.float32)).to(d)
         args = (ks, None, xs, torch.from_numpy(h).to(d), torch.from_numpy(g).to(d), 50)
         a = kernel.cc_backward(*args, precision=_prec("fp16x3"))
-        b = kernel.cc_backward(*args, precision=_prec("bf16x3"))
+        b = kernel.cc_backward(*args, precision=_prec("fp32"))
         torch.cuda.synchronize()
-        for ta, tb in zip(a[1:], b[1:]):
+        for ta in a[1:]:
             assert torch.isfinite(ta).all()
-            assert torch.equal(ta, tb) == same
+        if overflow:
+            assert torch.equal(a[1], b[1])                                                    # d_x = f(x) * g per slot
+            assert norm_err(a[3].cpu().numpy(), b[3].cpu().numpy()) < 1e-6                    # d_h
+            assert norm_err(a[2].cpu().numpy(), b[2].cpu().numpy()) < 1e-5                    # d_params
+        else:
+            assert not torch.equal(a[1], b[1])                                                # the fp16 result stands
+
+
+def test_bf16x3_is_a_diagnostic_precision_below_the_bar():
+    """UMNN_PREC_BF16X3 (never selected by AUTO) is kept for A/B measurements of the operand formats: it meets the
+    1e-5 bar on default-initialised networks but its ~17-bit operands measure 1e-5..2.2e-5 on trained-scale weights,
+    where FP16X3 holds 3e-6.  This test documents both facts; nothing in the product depends on BF16X3."""
+    spec = orc.MLPSpec((31, 200, 200, 200, 1))
+    x0, x, h, _ = orc.synth_inputs(64, 6, 180, 2, x0_zero=False)
+    for gain, bf16_bound in ((1.0, INTEGRAL_TOL), (2.5, 1e-4)):
+        flat = orc.synth_params(spec, 0, gain)
+        ref, _, _ = c_binding.cc_forward(spec, flat, x0, x, h, 50)
+        b, _, _ = _run_kernel(spec, flat, x0, x, h, 50, "strided", precision="bf16x3")
+        a, _, _ = _run_kernel(spec, flat, x0, x, h, 50, "strided", precision="fp16x3")
+        assert rel_err(b, ref) < bf16_bound
+        assert rel_err(a, ref) < INTEGRAL_TOL
+        if gain > 1.0:
+            assert rel_err(a, ref) < rel_err(b, ref)
 
 
 def test_packed_parameter_cache_tracks_updates():
@@ -397,22 +405,7 @@ def _oracle_backward_with_jac(spec, flat, inp, grad_fx):
     return d_x0, d_x, d_flat, d_h
 
 
-def _norm_err(a, ref):
-    return float(np.linalg.norm((a - ref).ravel()) / max(np.linalg.norm(ref.ravel()), 1e-30))
-
-
-def _grad_ok(a, ref, precision):
-    """FP32 backward: max error <= 1e-3 of the largest entry.  BF16x3 backward: the network is
-    re-evaluated with ~17.5-bit operands, so ~90x more LeakyReLU units sit within rounding noise of their kink
-    than in fp32; a flipped unit changes the gradient of its slot discontinuously (the reference's own fp32 vs
-    fp64 gradients show the same effect at 1.2e-4).  Those gradients are therefore held to a normwise bound
-    (<= 5e-3) plus a loose max bound (<= 5e-2 of the largest entry); the median error stays ~1e-6."""
-    if precision == "fp32":
-        return rel_to_max(a, ref) < GRAD_TOL
-    return _norm_err(a, ref) < 5e-3 and rel_to_max(a, ref) < 5e-2
-
-
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "fp16x3"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
 @pytest.mark.parametrize("with_jac", [False, True])
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_native_backward_matches_oracle(name, with_jac, precision):
@@ -430,18 +423,20 @@ def test_native_backward_matches_oracle(name, with_jac, precision):
     d_x0, d_x, d_flat, d_h = kernel.cc_backward(kspec, x0, x, h, go, inp["Q"], grad_fx=tgfx, precision=prec)
     torch.cuda.synchronize()
     r_x0, r_x, r_flat, r_h = _oracle_backward_with_jac(spec, flat, inp, grad_fx)
-    tol = _tol(precision, float(g["meta_gain"]))
-    assert rel_to_max(d_x0.cpu().numpy(), r_x0) < tol
-    if with_jac:
-        assert _grad_ok(d_x.cpu().numpy(), r_x, precision)
+    B, Dx, layout = inp["B"], inp["Dx"], inp["layout"]
+    margins = orc.kink_margins(spec, flat, inp["x0"], inp["x"], inp["h"], inp["Q"], layout)
+    assert rel_to_max(d_x0.cpu().numpy(), r_x0) < INTEGRAL_TOL
+    if with_jac:     # d_x carries grad_fx * df/dx(x, h): one more per-slot quantity that a kink flip at x changes
+        assert_slot_grad_ok(d_x.cpu().numpy(), r_x, margins, precision, (B, Dx, 1), what=f"{name} d_x")
     else:
-        assert rel_to_max(d_x.cpu().numpy(), r_x) < tol
-    assert _grad_ok(d_h.cpu().numpy(), r_h, precision)
-    assert _grad_ok(d_flat.cpu().numpy(), r_flat, precision)
+        assert rel_to_max(d_x.cpu().numpy(), r_x) < INTEGRAL_TOL
+    assert_slot_grad_ok(dh_to_slots(d_h.cpu().numpy(), B, Dx, layout), dh_to_slots(r_h, B, Dx, layout), margins, precision,
+                        (B, Dx, -1), what=f"{name} d_h")
+    assert_sum_grad_ok(d_flat.cpu().numpy(), r_flat, what=f"{name} d_params")
     if not with_jac:
         stride = int(g["meta_dflat_stride"])
-        assert _grad_ok(d_flat.cpu().numpy()[::stride], g["par_dflat"], precision)
-        assert _grad_ok(d_h.cpu().numpy(), g["par_dh"], precision)
+        assert_sum_grad_ok(d_flat.cpu().numpy()[::stride], g["par_dflat"], what=f"{name} d_params vs reference")
+        assert norm_err(d_h.cpu().numpy(), g["par_dh"]) < 2e-3
     # deterministic, and partial outputs may be skipped
     again = kernel.cc_backward(kspec, x0, x, h, go, inp["Q"], grad_fx=tgfx, precision=prec)
     assert torch.equal(again[2], d_flat) and torch.equal(again[3], d_h)
@@ -457,7 +452,7 @@ def test_native_backward_matches_oracle(name, with_jac, precision):
     (1, 1, 1, [8], 1, "contig"),                        # tiny everything
     (50, 1, 255, [256, 256], 7, "contig"),              # widest input / hidden layers
 ])
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "fp16x3"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
 def test_native_backward_shapes(B, D, E, hidden, Q, layout, precision):
     from umnn_b200 import kernel, _native
     spec = orc.MLPSpec(tuple([1 + E] + hidden + [1]), orc.HIDDEN_LEAKY if layout == "strided" else orc.HIDDEN_RELU)
@@ -476,15 +471,17 @@ def test_native_backward_shapes(B, D, E, hidden, Q, layout, precision):
     n_chk = min(B, 40)
     inp = dict(x0=x0[:n_chk], x=x[:n_chk], h=h[:n_chk], grad_out=go[:n_chk], Q=Q, layout=layout)
     r_x0, r_x, _, r_h = _oracle_backward_with_jac(spec, flat, inp, None)
-    tol = _tol(precision, 1.5)
+    tol = INTEGRAL_TOL
     assert rel_to_max(got[0][:n_chk].cpu().numpy(), r_x0) < tol
     assert rel_to_max(got[1][:n_chk].cpu().numpy(), r_x) < tol
-    assert _grad_ok(got[3][:n_chk].cpu().numpy(), r_h, precision)
+    margins = orc.kink_margins(spec, flat, x0[:n_chk], x[:n_chk], h[:n_chk], Q, layout)
+    assert_slot_grad_ok(dh_to_slots(got[3][:n_chk].cpu().numpy(), n_chk, D, layout), dh_to_slots(r_h, n_chk, D, layout), margins,
+                        precision, (n_chk, D, -1), what="d_h")
     # parameter gradient: the same batch through the torch route on the device
     from umnn_b200.integral import _integrate_grads_chunked
     ref_flat, _ = _integrate_grads_chunked(torch.from_numpy(x0).to(d), xd, net, torch.from_numpy(h).to(d), Q,
                                            torch.from_numpy(go).to(d), False)
-    assert _grad_ok(got[2].cpu().numpy(), ref_flat.detach().cpu().numpy(), precision)
+    assert_sum_grad_ok(got[2].cpu().numpy(), ref_flat.detach().cpu().numpy(), what="d_params vs torch ops")
 
 
 # ---- full-size configurations (BASELINE.json): sampled oracle checks + size-independent properties ----
@@ -500,8 +497,13 @@ def _full_size_check(B, D, E, hidden, Q, n_check, seed):
     out, fx, _ = cc_integrate(net, None, x, h, Q, want_fx=True)
     torch.cuda.synchronize()
     assert torch.isfinite(out).all() and torch.isfinite(fx).all() and (fx >= 0).all()
-    # (1) a random subset of samples against the C oracle
-    idx = torch.randperm(B, generator=torch.Generator().manual_seed(seed))[:n_check]
+    # (1) samples against the C oracle: contiguous runs at the start of the batch (first CTA's slot range), at its end
+    #     (last CTA, the ragged tail) and across the middle CTA boundary, plus a random subset
+    run = max(1, min(B, n_check) // 4)
+    mid = B // 2
+    picks = torch.cat([torch.arange(0, run), torch.arange(B - run, B), torch.arange(max(0, mid - run // 2), min(B, mid + run - run // 2)),
+                       torch.randperm(B, generator=torch.Generator().manual_seed(seed))[:run]])
+    idx = torch.unique(picks)
     xs, hs = x[idx.to(d)].cpu().numpy(), h[idx.to(d)].cpu().numpy()
     ref, rfx, _ = c_binding.cc_forward(spec, flat, np.zeros_like(xs), xs, hs, Q)
     assert rel_err(out[idx.to(d)].cpu().numpy(), ref) < INTEGRAL_TOL
@@ -519,7 +521,7 @@ def _full_size_check(B, D, E, hidden, Q, n_check, seed):
 
 
 def test_config3_full_size():
-    _full_size_check(10000, 6, 30, [200, 200, 200], 50, n_check=64, seed=3)
+    _full_size_check(10000, 6, 30, [200, 200, 200], 50, n_check=512, seed=3)
 
 
 def test_config2_full_size():
@@ -527,11 +529,11 @@ def test_config2_full_size():
 
 
 def test_config5_full_size():
-    _full_size_check(100, 784, 30, [100, 50, 50, 50, 50], 50, n_check=4, seed=5)
+    _full_size_check(100, 784, 30, [100, 50, 50, 50, 50], 50, n_check=24, seed=5)
 
 
 def test_config4_full_size():
-    _full_size_check(65536, 63, 30, [200, 200, 200], 100, n_check=4, seed=4)
+    _full_size_check(65536, 63, 30, [200, 200, 200], 100, n_check=384, seed=4)
 
 
 # ---- flows and the monotone regressor on the device ----------------------------------------------------
@@ -559,10 +561,10 @@ def test_flow_compute_ll_on_cuda_matches_reference():
     ll.sum().backward()
     assert np.max(np.abs(ll.detach().cpu().numpy() - g["ll"])) < 2e-5 * np.max(np.abs(g["ll"]))
     assert np.max(np.abs(z.detach().cpu().numpy() - g["z"])) < 2e-5 * max(1.0, np.max(np.abs(g["z"])))
-    assert _grad_ok(x.grad.cpu().numpy(), g["dx"], "auto")
+    assert norm_err(x.grad.cpu().numpy(), g["dx"]) < 2e-3 and rel_to_max(x.grad.cpu().numpy(), g["dx"]) < 2e-2
     for k, p in model.named_parameters():
         if p.grad is not None:
-            assert _grad_ok(p.grad.cpu().numpy(), g["grad/" + k], "auto"), k
+            assert_sum_grad_ok(p.grad.cpu().numpy(), g["grad/" + k], what=k)
     model.eval()
     with torch.no_grad():
         z_eval = model.forward(torch.from_numpy(xn).to(_dev()))
@@ -688,7 +690,7 @@ def test_training_curves_agree_between_backward_paths(monkeypatch):
 
     ref = train("fp32")
     assert ref[-1] < ref[0] - 0.1                                  # it actually trains
-    for mode in ("bf16x3", "auto"):                                # auto = fp16x3 re-evaluation, guarded
+    for mode in ("auto",):                                         # auto = fp16x3 re-evaluation, guarded
         tc = train(mode)
         assert np.max(np.abs(tc - ref)) < 2e-3 * max(1.0, np.max(np.abs(ref))), mode
 
@@ -712,8 +714,8 @@ def test_fused_flow_block_matches_unfused():
                      torch.cat([p.grad.reshape(-1) for p in blk.parameters() if p.grad is not None])))
     (z1, l1, gx1, gp1), (z2, l2, gx2, gp2) = outs
     assert torch.allclose(z1, z2, rtol=1e-5, atol=1e-5) and torch.allclose(l1, l2, rtol=1e-5, atol=1e-5)
-    assert _norm_err(gx1.cpu().numpy(), gx2.cpu().numpy()) < 5e-3
-    assert _norm_err(gp1.cpu().numpy(), gp2.cpu().numpy()) < 5e-3
+    assert norm_err(gx1.cpu().numpy(), gx2.cpu().numpy()) < 2e-3
+    assert norm_err(gp1.cpu().numpy(), gp2.cpu().numpy()) < 2e-3
 
 
 def test_cuda_graph_capture_and_replay():

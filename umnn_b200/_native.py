@@ -24,7 +24,7 @@ OUT_ELU_PLUS_1, OUT_SIGMOID = 0, 1
 PREC_FP32, PREC_BF16X3, PREC_AUTO, PREC_FP16X3 = 0, 1, 2, 3
 
 EXPORTS = ("umnn_abi_version", "umnn_last_error", "umnn_cc_tables", "umnn_param_count",
-           "umnn_packed_params_bytes", "umnn_pack_params", "umnn_workspace_bytes", "umnn_cc_forward",
+           "umnn_packed_params_bytes", "umnn_packed_layout_id", "umnn_pack_params", "umnn_workspace_bytes", "umnn_cc_forward",
            "umnn_cc_backward", "umnn_cc_forward_host", "umnn_invert_bracket_step", "umnn_tc_forward_occupancy")
 
 
@@ -71,6 +71,8 @@ def lib() -> ctypes.CDLL:
         L.umnn_param_count.argtypes = [dp]
         L.umnn_packed_params_bytes.restype = ctypes.c_size_t
         L.umnn_packed_params_bytes.argtypes = [dp]
+        L.umnn_packed_layout_id.restype = ctypes.c_uint64
+        L.umnn_packed_layout_id.argtypes = [dp]
         L.umnn_pack_params.restype = ctypes.c_int
         L.umnn_pack_params.argtypes = [dp, fp, vp, vp]
         L.umnn_workspace_bytes.restype = ctypes.c_size_t

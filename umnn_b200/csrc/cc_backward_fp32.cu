@@ -30,6 +30,7 @@ struct BwdParams {
     const float *x0, *x, *h, *packed, *nodes, *weights, *grad_out, *grad_fx;
     float *d_x0, *d_x, *d_h;
     float* scratch;
+    const int* run_if;      // not NULL: no-op unless *run_if != 0 (guarded re-run of an FP16X3 backward)
     long long slot0, n_slots_chunk, slots_per_cta, ld;
     int D, E, layout, Q, rps, n_layers, hidden_act, out_act;
     int nin[UMNN_MAX_LAYERS], nout[UMNN_MAX_LAYERS], kpad[UMNN_MAX_LAYERS], npad[UMNN_MAX_LAYERS];
@@ -93,6 +94,7 @@ __device__ __forceinline__ void gemm_tile(const float* in, const float* Wg, int 
 }
 
 __global__ void __launch_bounds__(512) cc_backward_fp32_kernel(const BwdParams p) {
+    if (p.run_if != nullptr && *p.run_if == 0) return;
     extern __shared__ __align__(16) float smem[];
     float* act = smem;                                  // activation buffers, act_off[l]
     float* wst = act + p.act_floats;                    // [2][kKC][max_w]
@@ -329,7 +331,8 @@ constexpr int kWP = kWT + 4;
 // conflict-free float4; operands are transposed on the way in ([dim][rows] panels -> [r][dim] tiles)
 __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ dz, const float* __restrict__ a, long long ld,
                                                     long long rows, long long slab, int nout, int nin, float* __restrict__ part,
-                                                    long long part_stride, int w_dst, int b_dst) {
+                                                    long long part_stride, int w_dst, int b_dst, const int* __restrict__ run_if) {
+    if (run_if != nullptr && *run_if == 0) return;
     __shared__ __align__(16) float As[2][kWK][kWP];   // [stage][r][n]
     __shared__ __align__(16) float Bs[2][kWK][kWP];   // [stage][r][k]
     const int tid = threadIdx.x;
@@ -432,7 +435,8 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ dz
 }
 
 __global__ void reduce_partials_kernel(const float* __restrict__ part, long long part_stride, int nsplit, long long P,
-                                       float* __restrict__ d_params, int accumulate) {
+                                       float* __restrict__ d_params, int accumulate, const int* __restrict__ run_if) {
+    if (run_if != nullptr && *run_if == 0) return;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     float s = accumulate ? d_params[i] : 0.0f;
@@ -453,7 +457,7 @@ struct BwdPlan {
     int threads;
 };
 
-bool make_plan(const umnn_desc* d, BwdPlan* B) {
+bool make_plan(const umnn_desc* d, BwdPlan* B, size_t budget_bytes = 0) {
     B->L = make_fp32_layout(d);
     const Fp32Layout& L = B->L;
     B->P = 0;
@@ -466,7 +470,18 @@ bool make_plan(const umnn_desc* d, BwdPlan* B) {
     const long long n_slots = d->n_samples * (long long)d->n_dims;
     // a chunk = n_cta x s whole slots, s chosen so that s*rps fills its 64-row tiles with the least padding
     const int n_cta = 148;
-    const long long per_cta_target = kChunkRowsTarget / n_cta;
+    long long rows_target = kChunkRowsTarget;
+    if (budget_bytes > 0) {
+        // chunks as large as the given workspace allows (never below the default)
+        const size_t fixed = (size_t)kMaxSplit * B->P * sizeof(float) + 1024;
+        if (budget_bytes > fixed) {
+            const long long fit = (long long)((budget_bytes - fixed) / ((size_t)B->floats_per_row * sizeof(float))) - 8;
+            if (fit > rows_target) rows_target = fit;
+        }
+        const long long all_rows = n_slots * B->rps;
+        if (rows_target > all_rows + n_cta * (long long)B->rps) rows_target = all_rows + n_cta * (long long)B->rps;
+    }
+    const long long per_cta_target = rows_target / n_cta;
     long long s_max = per_cta_target / B->rps;
     if (s_max < 1) s_max = 1;
     long long best_s = s_max;
@@ -514,18 +529,18 @@ const char* backward_fp32_unsupported_reason(const umnn_desc* d) {
     return nullptr;
 }
 
-size_t backward_fp32_workspace_bytes(const umnn_desc* d) {
+size_t backward_fp32_workspace_bytes(const umnn_desc* d, size_t budget_bytes) {
     BwdPlan B;
-    if (!make_plan(d, &B)) return 0;
+    if (!make_plan(d, &B, budget_bytes)) return 0;
     return B.total_bytes;
 }
 
 int launch_backward_fp32(const umnn_desc* d, const float* x0, const float* x, const float* h, const float* packed,
                          const float* nodes, const float* weights, const float* grad_out, const float* grad_fx,
                          float* d_x0, float* d_x, float* d_h, float* d_params, void* workspace, size_t workspace_bytes,
-                         cudaStream_t s) {
+                         cudaStream_t s, const int* run_if, size_t budget_bytes) {
     BwdPlan B;
-    if (!make_plan(d, &B)) {
+    if (!make_plan(d, &B, budget_bytes)) {
         set_error("umnn_cc_backward: %s", backward_fp32_unsupported_reason(d));
         return UMNN_ERR_UNSUPPORTED;
     }
@@ -546,6 +561,7 @@ int launch_backward_fp32(const umnn_desc* d, const float* x0, const float* x, co
     BwdParams p{};
     p.x0 = x0; p.x = x; p.h = h; p.packed = packed; p.nodes = nodes; p.weights = weights;
     p.grad_out = grad_out; p.grad_fx = grad_fx; p.d_x0 = d_x0; p.d_x = d_x; p.d_h = d_h; p.scratch = scratch;
+    p.run_if = run_if;
     p.D = d->n_dims; p.E = d->n_ctx; p.layout = d->layout; p.Q = d->nb_steps; p.rps = B.rps;
     p.n_layers = d->n_layers; p.hidden_act = d->hidden_act; p.out_act = d->out_act;
     p.ld = B.ld; p.act_floats = B.act_floats; p.max_w = B.max_w;
@@ -582,10 +598,10 @@ int launch_backward_fp32(const umnn_desc* d, const float* x0, const float* x, co
             for (int l = 0; l < d->n_layers; ++l) {
                 dim3 g((L.nin[l] + 1 + kWT - 1) / kWT, (L.nout[l] + kWT - 1) / kWT, nsplit);
                 wgrad_kernel<<<g, 256, 0, s>>>(scratch + p.dz_panel[l], scratch + p.a_panel[l], B.ld, rows, slab, L.nout[l],
-                                                L.nin[l], part, B.P, L.src_w_off[l], L.src_b_off[l]);
+                                                L.nin[l], part, B.P, L.src_w_off[l], L.src_b_off[l], run_if);
                 UMNN_CUDA_TRY(cudaGetLastError());
             }
-            reduce_partials_kernel<<<(unsigned)((B.P + 255) / 256), 256, 0, s>>>(part, B.P, nsplit, B.P, d_params, first ? 0 : 1);
+            reduce_partials_kernel<<<(unsigned)((B.P + 255) / 256), 256, 0, s>>>(part, B.P, nsplit, B.P, d_params, first ? 0 : 1, run_if);
             UMNN_CUDA_TRY(cudaGetLastError());
         }
         first = false;

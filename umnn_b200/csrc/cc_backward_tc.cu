@@ -20,6 +20,9 @@
 #include "tc_common.cuh"
 #include "tc_kernels.cuh"
 
+#include <stdlib.h>
+#include <string.h>
+
 namespace umnn {
 
 namespace {
@@ -56,6 +59,7 @@ struct TcDgradParams {
     float *d_x0, *d_x, *d_h;
     long long slot0, n_slots, slots_per_cta, row_block;
     int tiles_per_cta, D, E, layout, Q, rps, out_act;
+    int dz_parts;                              // parts of the dz panels: 1 = hi only, 2 = hi + lo
     const int* run_if;                         // not NULL: no-op unless *run_if != 0 (guarded bf16 re-run)
     TcDgradLayout L;
     TcDgradSmem S;
@@ -68,13 +72,16 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"r"(kEpiThreads) : "memory"); }
 
-__device__ __forceinline__ void emit16(const PanelRow& R, int col, const uint32_t (&o)[16]) {
+// the chain needs hi AND lo of dz for its own MMAs, so both exist in registers; the panel keeps `parts` of them
+__device__ __forceinline__ void emit16(const PanelRow& R, int col, const uint32_t (&o)[16], int parts) {
     uint8_t* g0 = R.base + panel_granule(R, col);
     uint8_t* g1 = R.base + panel_granule(R, col + 8);
     *reinterpret_cast<uint4*>(g0) = make_uint4(o[0], o[1], o[2], o[3]);
     *reinterpret_cast<uint4*>(g1) = make_uint4(o[4], o[5], o[6], o[7]);
-    *reinterpret_cast<uint4*>(g0 + R.lo_off) = make_uint4(o[8], o[9], o[10], o[11]);
-    *reinterpret_cast<uint4*>(g1 + R.lo_off) = make_uint4(o[12], o[13], o[14], o[15]);
+    if (parts == 2) {
+        *reinterpret_cast<uint4*>(g0 + R.lo_off) = make_uint4(o[8], o[9], o[10], o[11]);
+        *reinterpret_cast<uint4*>(g1 + R.lo_off) = make_uint4(o[12], o[13], o[14], o[15]);
+    }
 }
 
 // v * act'(.) for column c (0..31) of a pair from the recorded sign mask (set bit = negative pre-activation)
@@ -229,10 +236,12 @@ __global__ void __launch_bounds__(kThreads, 1) cc_dgrad_tc_kernel(const __grid_c
                 // dz_{J+1} panel (width 16): column 0 = dv
                 uint32_t hi, lo2;
                 split_bf16x2(dv, 0.0f, hi, lo2);
-                *reinterpret_cast<uint4*>(p.dz[J + 1] + panel_offset(pr, 0, 16, 0)) = make_uint4(hi, 0u, 0u, 0u);
-                *reinterpret_cast<uint4*>(p.dz[J + 1] + panel_offset(pr, 8, 16, 0)) = make_uint4(0u, 0u, 0u, 0u);
-                *reinterpret_cast<uint4*>(p.dz[J + 1] + panel_offset(pr, 0, 16, 1)) = make_uint4(lo2, 0u, 0u, 0u);
-                *reinterpret_cast<uint4*>(p.dz[J + 1] + panel_offset(pr, 8, 16, 1)) = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(p.dz[J + 1] + panel_offset(pr, 0, 16, 0, p.dz_parts)) = make_uint4(hi, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(p.dz[J + 1] + panel_offset(pr, 8, 16, 0, p.dz_parts)) = make_uint4(0u, 0u, 0u, 0u);
+                if (p.dz_parts == 2) {
+                    *reinterpret_cast<uint4*>(p.dz[J + 1] + panel_offset(pr, 0, 16, 1, 2)) = make_uint4(lo2, 0u, 0u, 0u);
+                    *reinterpret_cast<uint4*>(p.dz[J + 1] + panel_offset(pr, 8, 16, 1, 2)) = make_uint4(0u, 0u, 0u, 0u);
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[BAR_PREP_FULL + b]);
@@ -256,7 +265,7 @@ __global__ void __launch_bounds__(kThreads, 1) cc_dgrad_tc_kernel(const __grid_c
             const float dv = dvrow[bu * kTcTile + r];
             const uint32_t bits = p.mask[J][pr * 8 + pp];
             const int halves = (32 * pp + 16 < PJ) ? 2 : 1;
-            const PanelRow prow = panel_row(p.dz[J], pr, PJ);
+            const PanelRow prow = panel_row(p.dz[J], pr, PJ, p.dz_parts);
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
                 if (hf < halves) {
@@ -269,7 +278,7 @@ __global__ void __launch_bounds__(kThreads, 1) cc_dgrad_tc_kernel(const __grid_c
                         split_bf16x2(z0, z1, o[i], o[8 + i]);
                     }
                     tmem_st16(tbase + lane_sel + kColQ + 32u * pp + 16u * hf, o);
-                    emit16(prow, 32 * pp + 16 * hf, o);
+                    emit16(prow, 32 * pp + 16 * hf, o, p.dz_parts);
                 }
             }
             tmem_st_wait();
@@ -305,20 +314,20 @@ __global__ void __launch_bounds__(kThreads, 1) cc_dgrad_tc_kernel(const __grid_c
                     tmem_ld16(taddr, v0);
                     if (two) tmem_ld16(taddr + 16, v1);
                     tmem_ld_wait();
-                    const PanelRow prow = panel_row(p.dz[jout], pr, y.npad);
+                    const PanelRow prow = panel_row(p.dz[jout], pr, y.npad, p.dz_parts);
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
                         split_bf16x2(times_slope<HIDDEN_ACT>(__uint_as_float(v0[2 * i]), bits, 2 * i),
                                      times_slope<HIDDEN_ACT>(__uint_as_float(v0[2 * i + 1]), bits, 2 * i + 1), o[i], o[8 + i]);
                     tmem_st16(taddr, o);
-                    emit16(prow, 32 * pp, o);
+                    emit16(prow, 32 * pp, o, p.dz_parts);
                     if (two) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
                             split_bf16x2(times_slope<HIDDEN_ACT>(__uint_as_float(v1[2 * i]), bits, 16 + 2 * i),
                                          times_slope<HIDDEN_ACT>(__uint_as_float(v1[2 * i + 1]), bits, 17 + 2 * i), o[i], o[8 + i]);
                         tmem_st16(taddr + 16, o);
-                        emit16(prow, 32 * pp + 16, o);
+                        emit16(prow, 32 * pp + 16, o, p.dz_parts);
                     }
                     tmem_st_wait();
                     tc_fence_before_sync();
@@ -465,7 +474,7 @@ __global__ void pack_dgrad_consts_kernel(const float* __restrict__ flat, uint8_t
 // ------------------------------------------------------------------------------------------------------
 // pass W
 // ------------------------------------------------------------------------------------------------------
-constexpr int kWMaxStages = 5;
+constexpr int kWMaxStages = 8;
 constexpr int kWEpiWarps = 4;
 constexpr int kWThreads = (kWEpiWarps + 2) * 32;   // warps 0-3 epilogue, 4 producer, 5 MMA
 
@@ -534,11 +543,11 @@ __global__ void __launch_bounds__(kWThreads, 1) cc_wgrad_tc_kernel(const __grid_
         if (lane == 0) {
             uint32_t n = 0, bytes = 0;
             for (int pn = 0; pn < W.n_panels; ++pn) {
-                const int Wd = W.panel_width[pn];
+                const int Wd = W.panel_width[pn], parts = W.panel_parts[pn];
                 cp_dst[n] = W.tile_off[pn];
-                cp_src[n] = (unsigned long long)(p.panel[pn] + (size_t)rank * (size_t)(32 * Wd));   // this CTA's column half
-                cp_blk_stride[n] = (unsigned long long)(64 * Wd);
-                cp_bytes[n] = 32u * (uint32_t)Wd;                                               // hi + lo, both K halves
+                cp_src[n] = (unsigned long long)(p.panel[pn] + (size_t)rank * (size_t)(16 * Wd * parts));   // this CTA's column half
+                cp_blk_stride[n] = (unsigned long long)(32 * Wd * parts);
+                cp_bytes[n] = 16u * (uint32_t)(Wd * parts);                                     // hi [+ lo], both K halves
                 bytes += cp_bytes[n];
                 ++n;
             }
@@ -583,10 +592,12 @@ __global__ void __launch_bounds__(kWThreads, 1) cc_wgrad_tc_kernel(const __grid_
                     const uint64_t b_hi = make_smem_desc(stage_addr + W.tile_off[y.n_panel], lbo_n, 128);
                     const uint64_t b_lo = make_smem_desc(stage_addr + W.tile_off[y.n_panel] + 16u * y.n_width, lbo_n, 128);
                     const uint32_t d_addr = tbase + (uint32_t)y.tmem_col;
+                    // hi*hi always; the cross terms only for operands whose panel carries a lo part
+                    const bool m_lo = W.panel_parts[y.m_panel] == 2, n_lo = W.panel_parts[y.n_panel] == 2;
                     if (elect_one_sync()) {
                         mma_ss<2>(d_addr, a_hi, b_hi, idesc, kb > 0);
-                        mma_ss<2>(d_addr, a_lo, b_hi, idesc, 1);
-                        mma_ss<2>(d_addr, a_hi, b_lo, idesc, 1);
+                        if (m_lo) mma_ss<2>(d_addr, a_lo, b_hi, idesc, 1);
+                        if (n_lo) mma_ss<2>(d_addr, a_hi, b_lo, idesc, 1);
                     }
                     __syncwarp();
                 }
@@ -653,7 +664,15 @@ __global__ void reduce_partials_tc_kernel(const float* __restrict__ part, long l
 // ------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------
+BwdPanels bwd_panels() {
+    const char* e = getenv("UMNN_B200_BWD_PANELS");
+    if (e && strcmp(e, "hilo") == 0) return BwdPanels{2, 2};
+    if (e && strcmp(e, "a_hilo") == 0) return BwdPanels{2, 1};
+    return BwdPanels{1, 1};
+}
+
 struct BwdTcPlan {
+    BwdPanels panels;
     TcLayout F;            // forward layout (pass F blobs)
     TcDgradLayout G;
     TcWgradPlan W;
@@ -671,7 +690,8 @@ const char* make_bwd_plan(const umnn_desc* d, BwdTcPlan* B) {
     const bool two = tc_two_segments_public();
     if (!make_tc_layout(d, &B->F, two)) return "needs >= 2 hidden layers of width <= 254";
     if (!make_tc_dgrad_layout(d, &B->G, two)) return "input width (1 + E) above 62 or hidden width above 254";
-    if (!make_tc_wgrad_plan(B->G, &B->W)) return "weight-gradient accumulators exceed 512 TMEM columns";
+    B->panels = bwd_panels();
+    if (!make_tc_wgrad_plan(B->G, &B->W, B->panels)) return "weight-gradient accumulators exceed 512 TMEM columns";
     B->rps = d->nb_steps + 3;
     const TcSmem FS = make_tc_smem(B->F, B->rps, d->nb_steps);
     if (FS.total > kTcMaxSmem) return "forward weights + per-tile context do not fit in 227 KB of shared memory";
@@ -718,7 +738,7 @@ const char* make_bwd_plan(const umnn_desc* d, BwdTcPlan* B) {
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
     for (int pn = 0; pn < B->W.n_panels; ++pn) {
-        B->panel_bytes[pn] = (size_t)B->R_pad * B->W.panel_width[pn] * 4;      // hi + lo
+        B->panel_bytes[pn] = (size_t)B->R_pad * B->W.panel_width[pn] * 2 * B->W.panel_parts[pn];
         B->off_panel[pn] = take(B->panel_bytes[pn]);
     }
     for (int j = 1; j <= B->G.J; ++j) B->off_mask[j] = take((size_t)B->R_pad * 8 * 4);
@@ -748,12 +768,14 @@ size_t backward_tc_packed_bytes(const umnn_desc* d) {
     return 2 * (size_t)B.F.blob_bytes + 2 * (size_t)B.G.blob_bytes;
 }
 
-int launch_pack_backward_tc(const umnn_desc* d, const float* flat, void* packed, cudaStream_t s) {
+int launch_pack_backward_tc(const umnn_desc* d, const float* flat, void* packed, bool with_forward, cudaStream_t s) {
     BwdTcPlan B;
     const char* why = make_bwd_plan(d, &B);
     if (why) { set_error("BF16X3 backward: %s", why); return UMNN_ERR_UNSUPPORTED; }
-    int rc = launch_pack_tc(d, flat, packed, UMNN_OPF_BF16, s);   // forward blobs first
-    if (rc) return rc;
+    if (with_forward) {
+        const int rc = launch_pack_tc(d, flat, packed, UMNN_OPF_BF16, s);   // forward blobs first
+        if (rc) return rc;
+    }
     uint8_t* g = (uint8_t*)packed + 2 * (size_t)B.F.blob_bytes;
     const uint32_t n_w = B.G.weights_bytes;
     pack_dgrad_weights_kernel<<<(n_w + 255) / 256, 256, 0, s>>>(flat, g, B.G);
@@ -766,7 +788,7 @@ int launch_pack_backward_tc(const umnn_desc* d, const float* flat, void* packed,
 int launch_backward_tc(const umnn_desc* d, const float* x0, const float* x, const float* h, const void* packed,
                        const float* nodes, const float* weights, const float* grad_out, const float* grad_fx,
                        float* d_x0, float* d_x, float* d_h, float* d_params, void* workspace, size_t workspace_bytes,
-                       const void* fwd_blobs_fp16, cudaStream_t s) {
+                       const void* fwd_blobs_fp16, int* flag, const float* rerun_fp32_packed, cudaStream_t s) {
     BwdTcPlan B;
     const char* why = make_bwd_plan(d, &B);
     if (why) { set_error("BF16X3 backward: %s", why); return UMNN_ERR_UNSUPPORTED; }
@@ -788,6 +810,7 @@ int launch_backward_tc(const umnn_desc* d, const float* x0, const float* x, cons
     }
     emit.v = reinterpret_cast<float*>(ws + B.off_v);
     emit.row_block = B.row_block;
+    emit.parts = B.panels.a_parts;
 
     TcDgradParams g{};
     g.x0 = x0; g.x = x; g.weights = weights; g.grad_out = grad_out; g.grad_fx = grad_fx;
@@ -800,6 +823,7 @@ int launch_backward_tc(const umnn_desc* d, const float* x0, const float* x, cons
     g.slots_per_cta = B.slots_per_cta; g.row_block = B.row_block; g.tiles_per_cta = B.tiles;
     g.D = d->n_dims; g.E = d->n_ctx; g.layout = d->layout; g.Q = d->nb_steps; g.rps = B.rps; g.out_act = d->out_act;
     g.L = B.G; g.S = B.GS;
+    g.dz_parts = B.panels.dz_parts;
 
     TcWgradParams w{};
     for (int pn = 0; pn < B.W.n_panels; ++pn) w.panel[pn] = ws + B.off_panel[pn];
@@ -824,10 +848,11 @@ int launch_backward_tc(const umnn_desc* d, const float* x0, const float* x, cons
     // LeakyReLU units flip side against the fp32 forward than with bf16's ~17).  Its panels stay bf16 (split from
     // the same fp32 activations): one tcgen05.mma cannot take an fp16 and a bf16 operand (illegal instruction on
     // B200), and the dz panels need bf16's exponent range.  An activation beyond the fp16 range raises the flag;
-    // the whole backward is then repeated with bf16 operands by a second sequence of launches that are no-ops
-    // while the flag is clear.
-    int* flag = reinterpret_cast<int*>(ws + B.off_flag);
-    const int n_attempts = fwd_blobs_fp16 ? 2 : 1;
+    // the whole backward is then repeated by a second sequence of launches that are no-ops while the flag is clear:
+    // the FP32 backward (rerun_fp32_packed given: the rare case gets the parity anchor's arithmetic) or, for shapes
+    // the FP32 backward cannot hold in shared memory, the same passes with bf16 operands.
+    if (fwd_blobs_fp16 && !flag) { set_error("umnn_cc_backward: FP16X3 needs the flag workspace"); return UMNN_ERR_WORKSPACE; }
+    const int n_attempts = (fwd_blobs_fp16 && !rerun_fp32_packed) ? 2 : 1;
     if (fwd_blobs_fp16) UMNN_CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), s));
     for (int attempt = 0; attempt < n_attempts; ++attempt) {
         const bool fp16_act = fwd_blobs_fp16 && attempt == 0;
@@ -872,6 +897,9 @@ int launch_backward_tc(const umnn_desc* d, const float* x0, const float* x, cons
             first = false;
         }
     }
+    if (fwd_blobs_fp16 && rerun_fp32_packed)
+        return launch_backward_fp32(d, x0, x, h, rerun_fp32_packed, nodes, weights, grad_out, grad_fx, d_x0, d_x, d_h, d_params,
+                                    workspace, workspace_bytes, s, flag, workspace_bytes);
     return 0;
 }
 

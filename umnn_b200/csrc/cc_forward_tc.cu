@@ -93,26 +93,31 @@ __device__ __forceinline__ float hact(float v) {
     return HIDDEN_ACT == UMNN_ACT_LEAKY_RELU ? fmaxf(v, v * kLeakySlope) : fmaxf(v, 0.0f);
 }
 
-// two 16-byte granules (16 columns) of a bf16 hi / lo panel: o[0..7] = hi pairs, o[8..15] = lo pairs
+// two 16-byte granules (16 columns) of a bf16 panel: o[0..7] = hi pairs, o[8..15] = lo pairs (PARTS == 2 only)
+template <int PARTS>
 __device__ __forceinline__ void emit16(const PanelRow& R, int col, const uint32_t (&o)[16]) {
     uint8_t* g0 = R.base + panel_granule(R, col);
     uint8_t* g1 = R.base + panel_granule(R, col + 8);
     *reinterpret_cast<uint4*>(g0) = make_uint4(o[0], o[1], o[2], o[3]);
     *reinterpret_cast<uint4*>(g1) = make_uint4(o[4], o[5], o[6], o[7]);
-    *reinterpret_cast<uint4*>(g0 + R.lo_off) = make_uint4(o[8], o[9], o[10], o[11]);
-    *reinterpret_cast<uint4*>(g1 + R.lo_off) = make_uint4(o[12], o[13], o[14], o[15]);
+    if constexpr (PARTS == 2) {
+        *reinterpret_cast<uint4*>(g0 + R.lo_off) = make_uint4(o[8], o[9], o[10], o[11]);
+        *reinterpret_cast<uint4*>(g1 + R.lo_off) = make_uint4(o[12], o[13], o[14], o[15]);
+    }
 }
 
 // One pair of activations -> hi / lo operand words in the launch's operand format (o_hi, o_lo) and, for pass F,
-// the bf16 hi / lo words of the panel (p_hi, p_lo; tcgen05 cannot mix an fp16 with a bf16 operand in one MMA, so
-// the panels that pass W multiplies with the bf16 dz panels are bf16 in every mode).  TRACK: keep the largest
-// |activation| converted to fp16 (networks whose hidden activation would swallow a NaN: ReLU).
-template <int OPF, bool EMIT, bool TRACK>
+// the bf16 words of the panel (p_hi and, with EMIT == 2, p_lo; tcgen05 cannot mix an fp16 with a bf16 operand in one
+// MMA, so the panels that pass W multiplies with the bf16 dz panels are bf16 in every mode).  EMIT = 0: no panels,
+// 1: hi-only panels, 2: hi + lo panels.  TRACK: keep the largest |activation| converted to fp16 (networks whose
+// hidden activation would swallow a NaN: ReLU).
+template <int OPF, int EMIT, bool TRACK>
 __device__ __forceinline__ void split_pair(float2 a, uint32_t& o_hi, uint32_t& o_lo, uint32_t& p_hi, uint32_t& p_lo, float& amax) {
     split2<OPF>(a, o_hi, o_lo);
-    if constexpr (EMIT) {
+    if constexpr (EMIT != 0) {
         if constexpr (OPF == UMNN_OPF_BF16) { p_hi = o_hi; p_lo = o_lo; }
-        else split2<UMNN_OPF_BF16>(a, p_hi, p_lo);
+        else if constexpr (EMIT == 2) split2<UMNN_OPF_BF16>(a, p_hi, p_lo);
+        else p_hi = pack_bf16x2(a.x, a.y);
     }
     if constexpr (TRACK) amax = fmaxf(fmaxf(amax, fabsf(a.x)), fabsf(a.y));
 }
@@ -128,14 +133,15 @@ __device__ __forceinline__ float2 hact2(float2 v) {
     }
 }
 
-template <int HIDDEN_ACT, bool EMIT, bool NARROW, int OPF>
+template <int HIDDEN_ACT, int EMIT, bool NARROW, int OPF>
 __global__ void __launch_bounds__(Shape<NARROW>::kThreads, Shape<NARROW>::kCtasPerSm)
 cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
     using C = Shape<NARROW>;
     constexpr int kEpiWarps = C::kEpiWarps, kColGroups = C::kColGroups, kPrepWarps = C::kPrepWarps;
     constexpr int kMmaWarp = C::kMmaWarp, kThreads = C::kThreads, kEpiThreads = C::kEpiThreads, kPrepThreads = C::kPrepThreads;
     constexpr uint32_t kColP = C::kColP, kColQ = C::kColQ;
-    static_assert(!(EMIT && NARROW), "pass F runs the wide shape");
+    static_assert(!(EMIT != 0 && NARROW), "pass F runs the wide shape");
+    constexpr int kParts = EMIT == 2 ? 2 : 1;   // parts of the activation panels (pass F)
     // fp16 operands overflow above 65504.  With LeakyReLU the resulting inf / -inf pair turns every unit of the next
     // layer -- and from there the row's output -- into NaN, which the finalize step sees for free; ReLU would map
     // that NaN to 0, so ReLU networks track the largest converted value instead.
@@ -345,8 +351,9 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
                         }
                         split_bf16x2(v2[0], v2[1], hi4[i], lo4[i]);
                     }
-                    *reinterpret_cast<uint4*>(p.emit.a[0] + panel_offset(pr, gidx * 8, W0, 0)) = make_uint4(hi4[0], hi4[1], hi4[2], hi4[3]);
-                    *reinterpret_cast<uint4*>(p.emit.a[0] + panel_offset(pr, gidx * 8, W0, 1)) = make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]);
+                    *reinterpret_cast<uint4*>(p.emit.a[0] + panel_offset(pr, gidx * 8, W0, 0, kParts)) = make_uint4(hi4[0], hi4[1], hi4[2], hi4[3]);
+                    if constexpr (EMIT == 2)
+                        *reinterpret_cast<uint4*>(p.emit.a[0] + panel_offset(pr, gidx * 8, W0, 1, kParts)) = make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]);
                 }
             }
             float* cv = cvec + (size_t)b * p.S.max_slots * L.npad1;
@@ -405,7 +412,7 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
             }
             tmem_st16(tbase + lane_sel + kColQ + 16u * c16, o);
             if (EMIT) {
-                emit16(panel_row(p.emit.a[1], cta_row0 + (long long)tile * kTcTile + r, L.npad1), 16 * c16, ob);
+                emit16<kParts>(panel_row(p.emit.a[1], cta_row0 + (long long)tile * kTcTile + r, L.npad1, kParts), 16 * c16, ob);
                 return sign_mask16(pre);
             }
             return 0u;
@@ -452,7 +459,7 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
                     const long long pr = cta_row0 + (long long)t * kTcTile + r;
                     PanelRow prow;
                     if (EMIT) {
-                        prow = panel_row(p.emit.a[m + 2], pr, y.npad);
+                        prow = panel_row(p.emit.a[m + 2], pr, y.npad, kParts);
                         // signs first: the accumulator registers die as they are converted below
                         p.emit.mask[m + 2][pr * 8 + pp] = sign_mask16(v0) | (two ? sign_mask16(v1) << 4 : 0u);
                     }
@@ -461,14 +468,14 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
                         split_pair<OPF, EMIT, kTrack>(hact2<HIDDEN_ACT>(make_float2(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]))),
                                                       o[i], o[8 + i], ob[i], ob[8 + i], amax);
                     tmem_st16(taddr, o);
-                    if (EMIT) emit16(prow, 32 * pp, ob);
+                    if (EMIT) emit16<kParts>(prow, 32 * pp, ob);
                     if (two) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
                             split_pair<OPF, EMIT, kTrack>(hact2<HIDDEN_ACT>(make_float2(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]))),
                                                           o[i], o[8 + i], ob[i], ob[8 + i], amax);
                         tmem_st16(taddr + 16, o);
-                        if (EMIT) emit16(prow, 32 * pp + 16, ob);
+                        if (EMIT) emit16<kParts>(prow, 32 * pp + 16, ob);
                     }
                     publish(m + 1, pp);
                 }
@@ -516,19 +523,23 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
                     if (EMIT) {
                         // last hidden activations a_J (operand of the output layer's weight gradient) and their signs
                         const long long pr = cta_row0 + (long long)t * kTcTile + r;
-                        const PanelRow prow = panel_row(p.emit.a[n_mma + 1], pr, L.npadL);
+                        const PanelRow prow = panel_row(p.emit.a[n_mma + 1], pr, L.npadL, kParts);
                         uint32_t o[16];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            split_bf16x2(hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i + 1])),
-                                         o[i], o[8 + i]);
-                        emit16(prow, 32 * pp, o);
+                        for (int i = 0; i < 8; ++i) {
+                            const float e0 = hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i])), e1 = hact<HIDDEN_ACT>(__uint_as_float(v0[2 * i + 1]));
+                            if constexpr (EMIT == 2) split_bf16x2(e0, e1, o[i], o[8 + i]);
+                            else o[i] = pack_bf16x2(e0, e1);
+                        }
+                        emit16<kParts>(prow, 32 * pp, o);
                         if (two) {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                split_bf16x2(hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i])), hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i + 1])),
-                                             o[i], o[8 + i]);
-                            emit16(prow, 32 * pp + 16, o);
+                            for (int i = 0; i < 8; ++i) {
+                                const float e0 = hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i])), e1 = hact<HIDDEN_ACT>(__uint_as_float(v1[2 * i + 1]));
+                                if constexpr (EMIT == 2) split_bf16x2(e0, e1, o[i], o[8 + i]);
+                                else o[i] = pack_bf16x2(e0, e1);
+                            }
+                            emit16<kParts>(prow, 32 * pp + 16, o);
                         }
                         p.emit.mask[n_mma + 1][pr * 8 + pp] = sign_mask16(v0) | (two ? sign_mask16(v1) << 4 : 0u);
                     }
@@ -710,7 +721,7 @@ bool tc_narrow_enabled() {
     return !(e && e[0] == '0');
 }
 
-template <bool EMIT, bool NARROW, int OPF>
+template <int EMIT, bool NARROW, int OPF>
 int launch_tc_kernel(int hidden_act, const TcParams& p, int n_cta, cudaStream_t s) {
     auto kern = hidden_act == UMNN_ACT_LEAKY_RELU ? cc_forward_tc_kernel<UMNN_ACT_LEAKY_RELU, EMIT, NARROW, OPF>
                                                   : cc_forward_tc_kernel<UMNN_ACT_RELU, EMIT, NARROW, OPF>;
@@ -803,10 +814,10 @@ int launch_forward_tc(const umnn_desc* d, const float* x0, const float* x, const
     p.tiles_per_cta = (int)((p.slots_per_cta * p.rps + kTcTile - 1) / kTcTile);
 
     if (opf == UMNN_OPF_FP16)
-        return narrow ? launch_tc_kernel<false, true, UMNN_OPF_FP16>(d->hidden_act, p, (int)n_cta, s)
-                      : launch_tc_kernel<false, false, UMNN_OPF_FP16>(d->hidden_act, p, (int)n_cta, s);
-    return narrow ? launch_tc_kernel<false, true, UMNN_OPF_BF16>(d->hidden_act, p, (int)n_cta, s)
-                  : launch_tc_kernel<false, false, UMNN_OPF_BF16>(d->hidden_act, p, (int)n_cta, s);
+        return narrow ? launch_tc_kernel<0, true, UMNN_OPF_FP16>(d->hidden_act, p, (int)n_cta, s)
+                      : launch_tc_kernel<0, false, UMNN_OPF_FP16>(d->hidden_act, p, (int)n_cta, s);
+    return narrow ? launch_tc_kernel<0, true, UMNN_OPF_BF16>(d->hidden_act, p, (int)n_cta, s)
+                  : launch_tc_kernel<0, false, UMNN_OPF_BF16>(d->hidden_act, p, (int)n_cta, s);
 }
 
 // diagnostic behind umnn_tc_forward_occupancy: which shape serves the descriptor and how many CTAs of it one SM holds
@@ -824,8 +835,8 @@ int tc_forward_occupancy(const umnn_desc* d, int extra_rows, int* narrow_out, in
     const bool narrow = tc_narrow_enabled() && tc_layout_is_narrow(L) && S.total <= kTcNarrowMaxSmem;
     if (narrow_out) *narrow_out = narrow ? 1 : 0;
     if (!ctas_per_sm) return 0;          // shape selection only: host arithmetic, no device needed
-    const void* kern = narrow ? (const void*)cc_forward_tc_kernel<UMNN_ACT_LEAKY_RELU, false, true, UMNN_OPF_FP16>
-                              : (const void*)cc_forward_tc_kernel<UMNN_ACT_LEAKY_RELU, false, false, UMNN_OPF_FP16>;
+    const void* kern = narrow ? (const void*)cc_forward_tc_kernel<UMNN_ACT_LEAKY_RELU, 0, true, UMNN_OPF_FP16>
+                              : (const void*)cc_forward_tc_kernel<UMNN_ACT_LEAKY_RELU, 0, false, UMNN_OPF_FP16>;
     UMNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
     if (narrow) UMNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     // the kernel is launched as clusters of 2: ask how many clusters the device holds at once
@@ -871,8 +882,11 @@ int launch_forward_tc_emit(const umnn_desc* d, const float* x0, const float* x, 
         set_error("BF16X3 backward: needs %u bytes of shared memory (max %zu)", p.S.total, kTcMaxSmem);
         return UMNN_ERR_UNSUPPORTED;
     }
-    return opf == UMNN_OPF_FP16 ? launch_tc_kernel<true, false, UMNN_OPF_FP16>(d->hidden_act, p, n_cta, s)
-                                : launch_tc_kernel<true, false, UMNN_OPF_BF16>(d->hidden_act, p, n_cta, s);
+    if (emit.parts == 2)
+        return opf == UMNN_OPF_FP16 ? launch_tc_kernel<2, false, UMNN_OPF_FP16>(d->hidden_act, p, n_cta, s)
+                                    : launch_tc_kernel<2, false, UMNN_OPF_BF16>(d->hidden_act, p, n_cta, s);
+    return opf == UMNN_OPF_FP16 ? launch_tc_kernel<1, false, UMNN_OPF_FP16>(d->hidden_act, p, n_cta, s)
+                                : launch_tc_kernel<1, false, UMNN_OPF_BF16>(d->hidden_act, p, n_cta, s);
 }
 
 bool tc_two_segments_public() { return tc_two_segments(); }

@@ -8,11 +8,19 @@
 // turns the bias gradient into one more column of the weight-gradient GEMM).  A_0 = [x_row, h_slot, 1, 0..]
 // has width P_0 = round_up(1 + E + 1, 16).
 //
-// A panel of width W stores bf16 hi AND lo values for R_pad rows in blocks of 16 rows.  In pass W every panel
-// is one operand of one cta_group::2 MMA, whose two CTAs each supply half of the columns, so a block is laid
-// out as  [column half (2)][part hi/lo][k8 = (row % 16) / 8][col8][row % 8][col % 8]:  each CTA fetches its half
-// of a block (hi + lo, 64 * W/2 bytes, contiguous) with ONE bulk-TMA copy and the result is directly a pair of
-// MN-major UMMA operand tiles (128-byte core matrices; LBO = (W/16)*128 between the K halves, SBO = 128).
+// A panel of width W stores, for R_pad rows in blocks of 16 rows, `parts` bf16 values per element: the rounded value
+// ("hi", parts = 1) or hi AND the residual lo (parts = 2).  In pass W every panel is one operand of one cta_group::2
+// MMA, whose two CTAs each supply half of the columns, so a block is laid out as
+//   [column half (2)][part (parts)][k8 = (row % 16) / 8][col8][row % 8][col % 8]:
+// each CTA fetches its half of a block (parts * 32 * W/2 bytes, contiguous) with ONE bulk-TMA copy and the result is
+// directly `parts` MN-major UMMA operand tiles (128-byte core matrices; LBO = (W/16)*128 between the K halves,
+// SBO = 128).
+//
+// Which panels carry a lo part is the backward's HBM-traffic / precision trade (BwdPanels below).  The panels only
+// feed the WEIGHT gradient dW = sum over rows of dz^T a: per-row rounding errors of a bf16 operand (2^-9 relative,
+// independent from row to row) average out over the millions of rows of the sum, so hi-only panels cost the weight
+// gradient ~1e-4..1e-3 normwise while halving the scratch (d_h, d_x and d_x0 never read a panel: the dgrad chain
+// keeps its 3-term hi/lo products in tensor memory).
 #pragma once
 
 #include "tc_layout.cuh"
@@ -22,11 +30,11 @@ namespace umnn {
 constexpr int kBwdMaxHidden = UMNN_MAX_LAYERS - 1;          // J <= 7
 constexpr int kBwdMaxTiles = 32;                            // tiles of 128 rows per CTA and chunk
 
-__host__ __device__ inline size_t panel_offset(long long pr, int c, int W, int part) {
+__host__ __device__ inline size_t panel_offset(long long pr, int c, int W, int part, int parts) {
     const int hw = W >> 1;                       // columns per CTA half (multiple of 8)
     const int half = c >= hw ? 1 : 0;
     const int cin = c - half * hw;
-    return (size_t)(pr >> 4) * (size_t)(64 * W) + (size_t)half * (size_t)(64 * hw) + (size_t)part * (size_t)(32 * hw) +
+    return (size_t)(pr >> 4) * (size_t)(32 * W * parts) + (size_t)half * (size_t)(32 * hw * parts) + (size_t)part * (size_t)(32 * hw) +
            (size_t)(((pr >> 3) & 1) * (hw >> 3) + (cin >> 3)) * 128 + (size_t)(pr & 7) * 16 + (size_t)(cin & 7) * 2;
 }
 
@@ -35,15 +43,15 @@ __host__ __device__ inline size_t panel_offset(long long pr, int c, int W, int p
 struct PanelRow {
     uint8_t* base;
     uint32_t hw;           // columns per CTA half
-    uint32_t half_off;     // extra offset of the second column half (64*hw - 16*hw)
-    uint32_t lo_off;       // offset of the lo part
+    uint32_t half_off;     // extra offset of the second column half (32*hw*parts - 16*hw)
+    uint32_t lo_off;       // offset of the lo part (parts == 2)
 };
-__host__ __device__ inline PanelRow panel_row(uint8_t* panel, long long pr, int W) {
+__host__ __device__ inline PanelRow panel_row(uint8_t* panel, long long pr, int W, int parts) {
     PanelRow R;
     const uint32_t hw = (uint32_t)W >> 1;
-    R.base = panel + (size_t)(pr >> 4) * (size_t)(64 * W) + (size_t)(((uint32_t)(pr >> 3) & 1u) * hw * 16u + ((uint32_t)pr & 7u) * 16u);
+    R.base = panel + (size_t)(pr >> 4) * (size_t)(32 * W * parts) + (size_t)(((uint32_t)(pr >> 3) & 1u) * hw * 16u + ((uint32_t)pr & 7u) * 16u);
     R.hw = hw;
-    R.half_off = 48u * hw;
+    R.half_off = 32u * hw * (uint32_t)parts - 16u * hw;
     R.lo_off = 32u * hw;
     return R;
 }
@@ -162,11 +170,16 @@ struct TcWgradLayer {
     int n_out, n_in, ones_col;  // true dims; column (or row when swapped) that carries the bias gradient
 };
 
+// parts per element of the activation panels (A_0..A_J) and of the dz panels (DZ_1..DZ_{J+1}): 1 = bf16 hi only,
+// 2 = hi + lo.  UMNN_B200_BWD_PANELS = hi (default: {1,1}) | a_hilo ({2,1}) | hilo ({2,2}: round 1's scheme).
+struct BwdPanels { int a_parts, dz_parts; };
+
 struct TcWgradPlan {
     int n_layers;               // = J + 1
     TcWgradLayer layer[UMNN_MAX_LAYERS];
     int n_panels;               // panel table: A_0..A_J then DZ_1..DZ_{J+1}
     int panel_width[2 * UMNN_MAX_LAYERS + 2];
+    int panel_parts[2 * UMNN_MAX_LAYERS + 2];
     uint32_t stage_bytes;       // bytes staged per 16-row K block and CTA (+ slack for the M-tile over-read)
     uint32_t tile_off[2 * UMNN_MAX_LAYERS + 2];      // smem offset of the panel's tile (hi, then lo) inside a stage
     int tmem_cols_used;
@@ -176,14 +189,15 @@ struct TcWgradPlan {
 inline int panel_A(int j) { return j; }                             // j = 0..J
 inline int panel_DZ(int j, int J) { return J + j; }                 // j = 1..J+1  -> J+1 .. 2J+1
 
-inline bool make_tc_wgrad_plan(const TcDgradLayout& G, TcWgradPlan* W) {
+inline bool make_tc_wgrad_plan(const TcDgradLayout& G, TcWgradPlan* W, BwdPanels pp = BwdPanels{1, 1}) {
     *W = TcWgradPlan{};
     const int J = G.J;
     W->n_layers = J + 1;
     W->n_panels = 2 * J + 2;
-    for (int j = 0; j <= J; ++j) W->panel_width[panel_A(j)] = G.P[j];
-    for (int j = 1; j <= J; ++j) W->panel_width[panel_DZ(j, J)] = G.P[j];
+    for (int j = 0; j <= J; ++j) { W->panel_width[panel_A(j)] = G.P[j]; W->panel_parts[panel_A(j)] = pp.a_parts; }
+    for (int j = 1; j <= J; ++j) { W->panel_width[panel_DZ(j, J)] = G.P[j]; W->panel_parts[panel_DZ(j, J)] = pp.dz_parts; }
     W->panel_width[panel_DZ(J + 1, J)] = 16;
+    W->panel_parts[panel_DZ(J + 1, J)] = pp.dz_parts;
     int col = 0;
     for (int j = 1; j <= J + 1; ++j) {
         TcWgradLayer& y = W->layer[j - 1];
@@ -209,7 +223,7 @@ inline bool make_tc_wgrad_plan(const TcDgradLayout& G, TcWgradPlan* W) {
     uint32_t off = 0;
     for (int p = 0; p < W->n_panels; ++p) {
         W->tile_off[p] = off;
-        off += 32u * (uint32_t)W->panel_width[p];          // hi + lo of half the columns, 16 rows
+        off += 16u * (uint32_t)W->panel_width[p] * (uint32_t)W->panel_parts[p];   // `parts` tiles of half the columns, 16 rows
     }
     // an M tile is read as 128 rows per K half although only W/2 are staged: the tensor core over-reads up to
     // (128 - 8) * 16 bytes past the last K half of the last tile -> keep that much slack inside the stage

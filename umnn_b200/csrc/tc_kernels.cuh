@@ -8,11 +8,12 @@ namespace umnn {
 
 // panels written by pass F (EMIT) for one chunk of rows; index j = hidden layer (0 = network input)
 struct TcEmit {
-    uint8_t* a[UMNN_MAX_LAYERS];       // A_j panels (bf16 hi and lo interleaved per block, see tc_bwd_layout.cuh)
+    uint8_t* a[UMNN_MAX_LAYERS];       // A_j panels (bf16 hi [and lo] per block, see tc_bwd_layout.cuh)
     uint32_t* mask[UMNN_MAX_LAYERS];   // [R_pad][8] sign bits per 32-column pair, j = 1..J
     float* v;                          // [R_pad] pre-output-activation
     int width[UMNN_MAX_LAYERS];        // panel widths P_j
     long long row_block;               // padded rows per CTA (tiles_per_cta * 128)
+    int parts;                         // 1: hi only, 2: hi + lo
 };
 
 struct TcParams {
@@ -48,10 +49,14 @@ bool tc_two_segments_public();
 const char* backward_tc_unsupported_reason(const umnn_desc* d);
 size_t backward_tc_workspace_bytes(const umnn_desc* d);
 size_t backward_tc_packed_bytes(const umnn_desc* d);      // bf16 forward blobs + dgrad blobs
-int launch_pack_backward_tc(const umnn_desc* d, const float* flat, void* packed, cudaStream_t s);
+// with_forward = false: only the dgrad blobs are written (an FP16X3 block whose re-run is the FP32 kernel never
+// reads the bf16 forward blobs)
+int launch_pack_backward_tc(const umnn_desc* d, const float* flat, void* packed, bool with_forward, cudaStream_t s);
+// fwd_blobs_fp16 != NULL: pass F re-evaluates with fp16 operands and raises *flag on overflow; the guarded re-run is
+// the FP32 backward on `rerun_fp32_packed` when that is given, else a second tensor-core sequence with bf16 operands
 int launch_backward_tc(const umnn_desc* d, const float* x0, const float* x, const float* h, const void* packed,
                        const float* nodes, const float* weights, const float* grad_out, const float* grad_fx,
                        float* d_x0, float* d_x, float* d_h, float* d_params, void* workspace, size_t workspace_bytes,
-                       const void* fwd_blobs_fp16, cudaStream_t s);
+                       const void* fwd_blobs_fp16, int* flag, const float* rerun_fp32_packed, cudaStream_t s);
 
 }  // namespace umnn

@@ -79,18 +79,11 @@ int validate_desc(const umnn_desc* d) {
     return 0;
 }
 
-// Which kernel family serves this descriptor.  UMNN_PREC_AUTO picks a tensor-core kernel whenever the shape fits
-// it (checked with the worst-case 2 extra rows per slot so that packing and launching agree), else the FP32
-// kernel.  Which split AUTO uses on the tensor cores is a process-wide choice: UMNN_B200_AUTO_TC = fp16x3
-// (default; guarded, see umnn_cc_forward) | bf16x3.  An explicit tensor-core precision on an unsupported shape fails.
-static int auto_tc_precision() {
-    const char* e = getenv("UMNN_B200_AUTO_TC");
-    if (e && (e[0] == 'b' || e[0] == 'B')) return UMNN_PREC_BF16X3;
-    return UMNN_PREC_FP16X3;
-}
-
+// Which kernel family serves this descriptor.  UMNN_PREC_AUTO picks the FP16X3 tensor-core kernel (guarded, see
+// umnn_cc_forward) whenever the shape fits it (checked with the worst-case 2 extra rows per slot so that packing and
+// launching agree), else the FP32 kernel.  An explicit tensor-core precision on an unsupported shape fails.
 static int resolve_precision(const umnn_desc* d) {
-    if (d->precision == UMNN_PREC_AUTO) return tc_unsupported_reason(d, 2) == nullptr ? auto_tc_precision() : UMNN_PREC_FP32;
+    if (d->precision == UMNN_PREC_AUTO) return tc_unsupported_reason(d, 2) == nullptr ? UMNN_PREC_FP16X3 : UMNN_PREC_FP32;
     return d->precision;
 }
 
@@ -106,15 +99,20 @@ static int check_tc(const umnn_desc* d, const char* who) {
 }
 
 // Packed block of the tensor-core precisions:
-//   [ bf16 forward blobs | dgrad blobs (when the tensor-core backward serves the shape) ]   UMNN_PREC_BF16X3
-//   [ the same, rounded up to 256 bytes | fp16 forward blobs ]                               UMNN_PREC_FP16X3
-// (the backward and the guarded re-run of an FP16X3 forward use the bf16 part)
+//   [ bf16 forward blobs | dgrad blobs (when the tensor-core backward serves the shape) ]              UMNN_PREC_BF16X3
+//   [ the same, rounded up to 256 bytes | fp16 forward blobs | (256-byte aligned) FP32 block ]          UMNN_PREC_FP16X3
+// Under FP16X3 the dgrad blobs (bf16) serve passes D of the backward and the FP32 block serves the guarded re-run
+// of a call whose activations left the fp16 range; the bf16 forward blobs are only filled in when the FP32
+// backward cannot hold the shape in shared memory (the backward's re-run then falls back to bf16 operands).
 static size_t tc_bf16_block_bytes(const umnn_desc* d) {
     return backward_tc_unsupported_reason(d) ? tc_packed_bytes(d) : backward_tc_packed_bytes(d);
 }
 static size_t tc_fp16_offset(const umnn_desc* d) { return (tc_bf16_block_bytes(d) + 255) / 256 * 256; }
+static size_t tc_fp32_offset(const umnn_desc* d) { return (tc_fp16_offset(d) + tc_packed_bytes(d) + 255) / 256 * 256; }
+// the backward's guarded re-run: FP32 kernels when they serve the shape, else the bf16 operand split
+static bool bwd_rerun_is_fp32(const umnn_desc* d) { return backward_fp32_unsupported_reason(d) == nullptr; }
 
-constexpr size_t kForwardFlagBytes = 256;   // workspace of a guarded FP16X3 forward: one int flag
+constexpr size_t kFlagBytes = 256;   // head of the workspace of a guarded FP16X3 call: one int flag
 
 }  // namespace umnn
 
@@ -165,9 +163,30 @@ size_t umnn_packed_params_bytes(const umnn_desc* d) {
             return tc_bf16_block_bytes(d);
         case UMNN_PREC_FP16X3:
             if (check_tc(d, "umnn_packed_params_bytes")) return 0;
-            return tc_fp16_offset(d) + tc_packed_bytes(d);
+            return tc_fp32_offset(d) + sizeof(float) * (size_t)make_fp32_layout(d).total_floats;
         default: return 0;
     }
+}
+
+uint64_t umnn_packed_layout_id(const umnn_desc* d) {
+    if (validate_desc(d) != 0) return 0;
+    const int prec = resolve_precision(d);
+    // FNV-1a over everything that decides where a kernel looks inside the packed block
+    uint64_t hsh = 1469598103934665603ull;
+    auto mix = [&](uint64_t v) { for (int i = 0; i < 8; ++i) { hsh ^= (v >> (8 * i)) & 0xffu; hsh *= 1099511628211ull; } };
+    mix((uint64_t)prec);
+    mix((uint64_t)umnn_packed_params_bytes(d));
+    mix((uint64_t)d->layout);
+    for (int l = 0; l <= d->n_layers; ++l) mix((uint64_t)d->widths[l]);
+    if (is_tc(prec) && tc_unsupported_reason(d, 2) == nullptr) {
+        mix((uint64_t)tc_two_segments_public());
+        mix((uint64_t)tc_bf16_block_bytes(d));
+        mix((uint64_t)tc_fp16_offset(d));
+        mix((uint64_t)tc_fp32_offset(d));
+        mix((uint64_t)(backward_tc_unsupported_reason(d) == nullptr));
+        mix((uint64_t)bwd_rerun_is_fp32(d));
+    }
+    return hsh ? hsh : 1;
 }
 
 int umnn_pack_params(const umnn_desc* d, const float* flat_params, void* params_packed, void* stream) {
@@ -181,10 +200,17 @@ int umnn_pack_params(const umnn_desc* d, const float* flat_params, void* params_
         case UMNN_PREC_BF16X3:
         case UMNN_PREC_FP16X3:
             if ((rc = check_tc(d, "umnn_pack_params")) != 0) return rc;
-            if (backward_tc_unsupported_reason(d)) rc = launch_pack_tc(d, flat_params, params_packed, UMNN_OPF_BF16, (cudaStream_t)stream);
-            else rc = launch_pack_backward_tc(d, flat_params, params_packed, (cudaStream_t)stream);
+            if (backward_tc_unsupported_reason(d)) {
+                // forward only: FP16X3 never reads the bf16 forward blobs (its re-run is the FP32 kernel)
+                rc = prec == UMNN_PREC_BF16X3 ? launch_pack_tc(d, flat_params, params_packed, UMNN_OPF_BF16, (cudaStream_t)stream) : 0;
+            } else {
+                const bool with_forward = prec == UMNN_PREC_BF16X3 || !bwd_rerun_is_fp32(d);
+                rc = launch_pack_backward_tc(d, flat_params, params_packed, with_forward, (cudaStream_t)stream);
+            }
             if (rc || prec == UMNN_PREC_BF16X3) return rc;
-            return launch_pack_tc(d, flat_params, (uint8_t*)params_packed + tc_fp16_offset(d), UMNN_OPF_FP16, (cudaStream_t)stream);
+            rc = launch_pack_tc(d, flat_params, (uint8_t*)params_packed + tc_fp16_offset(d), UMNN_OPF_FP16, (cudaStream_t)stream);
+            if (rc) return rc;
+            return launch_pack_fp32(d, flat_params, (float*)((uint8_t*)params_packed + tc_fp32_offset(d)), (cudaStream_t)stream);
         default:
             set_error("umnn_pack_params: precision %d is not available for this shape", d->precision);
             return UMNN_ERR_UNSUPPORTED;
@@ -193,14 +219,23 @@ int umnn_pack_params(const umnn_desc* d, const float* flat_params, void* params_
 
 size_t umnn_workspace_bytes(const umnn_desc* d, int32_t for_backward) {
     if (validate_desc(d) != 0) return 0;
-    if (!for_backward) return resolve_precision(d) == UMNN_PREC_FP16X3 ? kForwardFlagBytes : 0;
-    if (is_tc(resolve_precision(d))) {
+    const int prec = resolve_precision(d);
+    if (!for_backward) return prec == UMNN_PREC_FP16X3 ? kFlagBytes : 0;
+    if (is_tc(prec)) {
         const char* why = check_tc(d, "umnn_workspace_bytes") ? "forward shape unsupported" : backward_tc_unsupported_reason(d);
         if (why) {
             set_error("umnn_workspace_bytes: tensor-core backward unavailable for this shape (%s)", why);
             return 0;
         }
-        return backward_tc_workspace_bytes(d);
+        const size_t tc = backward_tc_workspace_bytes(d);
+        if (prec != UMNN_PREC_FP16X3) return tc;
+        // [flag | panels of the tensor-core passes, reused by the guarded FP32 re-run]
+        size_t body = tc;
+        if (bwd_rerun_is_fp32(d)) {
+            const size_t f = backward_fp32_workspace_bytes(d, tc);
+            if (f > body) body = f;
+        }
+        return kFlagBytes + body;
     }
     if (backward_fp32_unsupported_reason(d)) {
         set_error("umnn_workspace_bytes: backward unavailable for this shape (%s)", backward_fp32_unsupported_reason(d));
@@ -232,16 +267,17 @@ int umnn_cc_forward(const umnn_desc* d, const float* x0, const float* x, const f
     switch (resolve_precision(d)) {
         case UMNN_PREC_FP32:
             return launch_forward_fp32(d, x0, x, h, (const float*)params_packed, nodes, weights, out_integral,
-                                       out_f_at_x, out_f_at_x0, (cudaStream_t)stream);
+                                       out_f_at_x, out_f_at_x0, nullptr, (cudaStream_t)stream);
         case UMNN_PREC_BF16X3:
             if ((rc = check_tc(d, "umnn_cc_forward")) != 0) return rc;
             return launch_forward_tc(d, x0, x, h, params_packed, nodes, weights, out_integral, out_f_at_x,
                                      out_f_at_x0, UMNN_OPF_BF16, nullptr, nullptr, (cudaStream_t)stream);
         case UMNN_PREC_FP16X3: {
             // fp16 hi/lo operands carry 22 bits (bf16: ~17) but overflow above 65504.  Guarded: the kernel raises a
-            // device flag when an activation overflowed (every downstream value is NaN then), and a second launch of
-            // the bf16 kernel -- a no-op while the flag is clear -- recomputes the call.  Without a workspace the
-            // fp16 launch runs unguarded (overflow surfaces as NaN).
+            // device flag when an activation overflowed (every downstream value is NaN then), and a second launch --
+            // the FP32 FFMA kernel, a no-op while the flag is clear -- recomputes the call, so the rare overflow case
+            // gets the parity anchor's arithmetic, not a coarser split.  Without a workspace the fp16 launch runs
+            // unguarded (overflow surfaces as NaN).
             if ((rc = check_tc(d, "umnn_cc_forward")) != 0) return rc;
             const uint8_t* fp16_blobs = (const uint8_t*)params_packed + tc_fp16_offset(d);
             int* flag = nullptr;
@@ -252,8 +288,8 @@ int umnn_cc_forward(const umnn_desc* d, const float* x0, const float* x, const f
             rc = launch_forward_tc(d, x0, x, h, fp16_blobs, nodes, weights, out_integral, out_f_at_x, out_f_at_x0,
                                    UMNN_OPF_FP16, nullptr, flag, (cudaStream_t)stream);
             if (rc || !flag) return rc;
-            return launch_forward_tc(d, x0, x, h, params_packed, nodes, weights, out_integral, out_f_at_x, out_f_at_x0,
-                                     UMNN_OPF_BF16, flag, nullptr, (cudaStream_t)stream);
+            return launch_forward_fp32(d, x0, x, h, (const float*)((const uint8_t*)params_packed + tc_fp32_offset(d)), nodes,
+                                       weights, out_integral, out_f_at_x, out_f_at_x0, flag, (cudaStream_t)stream);
         }
         default:
             set_error("umnn_cc_forward: precision %d is not available for this shape", d->precision);
@@ -283,11 +319,20 @@ int umnn_cc_backward(const umnn_desc* d, const float* x0, const float* x, const 
     if (!x || !params_packed || !nodes || !weights || !grad_out || (d->n_ctx > 0 && !h)) {
         set_error("umnn_cc_backward: required pointer is NULL"); return UMNN_ERR_NULL;
     }
+    if (prec == UMNN_PREC_FP16X3) {
+        if (!workspace || workspace_bytes < umnn_workspace_bytes(d, 1)) {
+            set_error("umnn_cc_backward: workspace of %zu bytes needed, %zu given", umnn_workspace_bytes(d, 1), workspace_bytes);
+            return UMNN_ERR_WORKSPACE;
+        }
+        uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+        const float* fp32_block = bwd_rerun_is_fp32(d) ? (const float*)((const uint8_t*)params_packed + tc_fp32_offset(d)) : nullptr;
+        return launch_backward_tc(d, x0, x, h, params_packed, nodes, weights, grad_out, grad_f_at_x, d_x0, d_x, d_h, d_params,
+                                  ws + kFlagBytes, workspace_bytes - kFlagBytes, (const uint8_t*)params_packed + tc_fp16_offset(d),
+                                  reinterpret_cast<int*>(ws), fp32_block, (cudaStream_t)stream);
+    }
     if (is_tc(prec))
         return launch_backward_tc(d, x0, x, h, params_packed, nodes, weights, grad_out, grad_f_at_x, d_x0, d_x, d_h, d_params,
-                                  workspace, workspace_bytes,
-                                  prec == UMNN_PREC_FP16X3 ? (const uint8_t*)params_packed + tc_fp16_offset(d) : nullptr,
-                                  (cudaStream_t)stream);
+                                  workspace, workspace_bytes, nullptr, nullptr, nullptr, (cudaStream_t)stream);
     return launch_backward_fp32(d, x0, x, h, (const float*)params_packed, nodes, weights, grad_out, grad_f_at_x, d_x0, d_x,
                                 d_h, d_params, workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -87,11 +87,16 @@ class UMNNMAF(nn.Module):
         nets = self.net.parallel_nets
         tracing = torch.jit.is_tracing() or torch.jit.is_scripting()
         if tracing or ((not self.training) and (not x.requires_grad)):
-            # value only: no custom backward needed (UMNNMAF.py:89-106)
-            tables_ok = parallel and self.cc_weights.shape[0] == self.nb_steps + 1
-            return integral_nograd(x0, x, nets, h, self.nb_steps, parallel=parallel,
-                                   cc_weights=self.cc_weights if tables_ok else None,
-                                   steps=self.cc_steps if tables_ok else None)
+            # the reference integrates directly here (UMNNMAF.py:89-106): plain torch ops, which stay differentiable
+            # with respect to the integrand's parameters and h.  The fused kernel returns values only, so it serves
+            # this branch only when nothing can ask for a gradient; otherwise the autograd Function below does.
+            wants_grad = torch.is_grad_enabled() and (h.requires_grad or any(p.requires_grad for p in nets.parameters()))
+            on_kernel = (not tracing) and kernel_route(nets, x0, x, h) is not None
+            if not (on_kernel and wants_grad):
+                tables_ok = parallel and self.cc_weights.shape[0] == self.nb_steps + 1
+                return integral_nograd(x0, x, nets, h, self.nb_steps, parallel=parallel,
+                                       cc_weights=self.cc_weights if tables_ok else None,
+                                       steps=self.cc_steps if tables_ok else None)
         fn = ParallelNeuralIntegral if parallel else NeuralIntegral
         return fn.apply(x0, x, nets, _flatten(nets.parameters()), h, self.nb_steps)
 
@@ -184,7 +189,7 @@ class UMNNMAF(nn.Module):
         dev = self.device
         grid = torch.arange(0, 1 + .5 / (n_grid - 1), 1 / (n_grid - 1)).to(dev)          # [10]
         derivative = ContiguousIntegrand(self.net.parallel_nets)
-        # UMNN_B200_INVERT=torch keeps the op-by-op loop below on CUDA (benchmarks, A/B checks)
+        # UMNN_B200_INVERT=torch keeps the reference-shaped op-by-op loop below (A/B checks of the fused bracket step)
         if iter >= 1 and B > 0 and z.dtype == torch.float32 and os.environ.get("UMNN_B200_INVERT", "") != "torch" and \
                 kernel_route(derivative, z[:, :1], z[:, :1], z) is not None:
             return self._invert_native(z, iter, context, derivative, grid)

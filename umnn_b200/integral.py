@@ -9,15 +9,19 @@ Behavioural spec (AWehenkel/UMNN @ 59118c14), written fresh:
 Two routes serve the same maths:
   kernel route   CUDA float32 tensors + a recognised integrand (IntegrandNetwork, IntegrandNN,
                  ContiguousIntegrand) + inv_f == False + not tracing  ->  ONE fused sm_100a launch
-                 through the C ABI (umnn_b200/_native.py).  If the native library is missing this
-                 raises; it never degrades to torch ops.
+                 through the C ABI (umnn_b200/_native.py).  If the native library is missing, or the
+                 recognised integrand is outside the kernels' limits (width > 256, > 8 Linear layers, a
+                 backward neither native kernel can hold), this RAISES; it never degrades to torch ops on
+                 its own.  UMNN_B200_ALLOW_TORCH_ROUTE=1 turns those raises into the torch route.
   torch route    everything else the public API allows: arbitrary callables / lambdas, CPU or MPS
                  tensors, float64, TorchScript tracing, inv_f=True.  Same results as the reference.
+                 `with torch_route():` forces it for the calls inside (benchmarks of the reference's
+                 algorithm as PyTorch ops on the same device; never a default).
 """
 from __future__ import annotations
 
+import contextlib
 import os
-import warnings
 from typing import Optional, Tuple
 
 import torch
@@ -115,10 +119,14 @@ def _integrate_grads_chunked(x0, x, integrand, h, nb_steps, grad_output, inv_f):
         e = min(B, s + chunk)
         gp, gh = integrate(x0[s:e], nb_steps, (x[s:e] - x0[s:e]) / nb_steps, integrand, h[s:e], True,
                            grad_output[s:e], inv_f)
+        if not torch.is_grad_enabled():
+            # plain backward: drop each chunk's graph as soon as it is summed (bounded memory).  Under
+            # create_graph=True (double backward) the graphs are kept, as the reference keeps them.
+            gp = None if gp is None else gp.detach()
+            gh = gh.detach()
         if gp is not None:
-            gp = gp.detach()
             g_param_total = gp if g_param_total is None else g_param_total + gp
-        g_h_parts.append(gh.detach())
+        g_h_parts.append(gh)
     return g_param_total, torch.cat(g_h_parts, 0)
 
 
@@ -161,17 +169,40 @@ def computeIntegrand_sequential(x, h, integrand, x_tot):
 # --------------------------------------------------------------------------------------------------
 # dispatcher
 # --------------------------------------------------------------------------------------------------
-_warned = set()
+_forced_torch_route = 0
+
+
+@contextlib.contextmanager
+def torch_route():
+    """Inside this context every integral takes the torch route (the reference's algorithm as PyTorch ops on whatever
+    device the tensors live on).  A measurement / A-B tool: nothing in the product enters it."""
+    global _forced_torch_route
+    _forced_torch_route += 1
+    try:
+        yield
+    finally:
+        _forced_torch_route -= 1
+
+
+class UnsupportedIntegrandError(ValueError):
+    """A recognised integrand on CUDA float32 tensors that the native kernels cannot serve."""
+
+
+def _allow_torch_route() -> bool:
+    return os.environ.get("UMNN_B200_ALLOW_TORCH_ROUTE", "0") == "1"
 
 
 def kernel_route(integrand, x0, x, h, inv_f=False):
-    """The KernelSpec if this call is served by the fused CUDA kernel, else None."""
+    """The KernelSpec if this call is served by the fused CUDA kernel, else None (torch route).
+
+    A recognised integrand on CUDA float32 tensors never leaves the kernel route silently: outside the kernels'
+    limits this raises UnsupportedIntegrandError unless UMNN_B200_ALLOW_TORCH_ROUTE=1."""
     if inv_f or not (torch.is_tensor(x) and x.is_cuda):
         return None
     if torch.jit.is_tracing() or torch.jit.is_scripting():
         return None
-    if os.environ.get("UMNN_B200_ROUTE", "") == "torch":
-        return None     # measurement knob: the reference's algorithm as torch ops on the same device (never a default)
+    if _forced_torch_route:
+        return None
     get_spec = getattr(integrand, "kernel_spec", None)
     if not callable(get_spec):
         return None
@@ -182,12 +213,11 @@ def kernel_route(integrand, x0, x, h, inv_f=False):
         return None
     why = spec.supported()
     if why is not None:
-        key = (type(integrand).__name__, why)
-        if key not in _warned:
-            _warned.add(key)
-            warnings.warn(f"umnn_b200: {type(integrand).__name__} is outside the fused kernel's limits ({why}); "
-                          "using the torch route", RuntimeWarning)
-        return None
+        if _allow_torch_route():
+            return None
+        raise UnsupportedIntegrandError(
+            f"umnn_b200: {type(integrand).__name__} is outside the fused kernel's limits ({why}). "
+            "Set UMNN_B200_ALLOW_TORCH_ROUTE=1 to evaluate it with PyTorch ops instead.")
     if not (x0.is_cuda and h.is_cuda and x0.device == x.device and h.device == x.device):
         raise ValueError("umnn_b200: x0, x and h must live on the same CUDA device")
     for p in spec.parameters():
@@ -219,6 +249,10 @@ def _forward_common(ctx, x0, x, integrand, h, nb_steps, inv_f, parallel):
             # the Leibniz terms taken from extra rows of the forward launch
             ctx.bwd_precision = kernel.backward_precision(spec, x, nb_steps) if any(need) else None
             ctx.native_bwd = ctx.bwd_precision is not None
+            if any(need) and not ctx.native_bwd and not _allow_torch_route():
+                raise UnsupportedIntegrandError(
+                    "umnn_b200: neither native backward can hold this integrand shape in shared memory; set "
+                    "UMNN_B200_ALLOW_TORCH_ROUTE=1 to differentiate it with PyTorch ops instead.")
             want_fx = bool(need[1]) and not ctx.native_bwd
             want_fx0 = bool(need[0]) and not ctx.native_bwd
             out, fx, fx0 = kernel.cc_forward(spec, x0, x, h, nb_steps, want_fx=want_fx, want_fx0=want_fx0)
@@ -253,8 +287,8 @@ def _backward_common(ctx, grad_output, parallel):
         d_x0 = -fx0 * grad_output if fx0 is not None else None
         d_flat = d_h = None
         if need[3] or need[4]:
-            # shapes the fused backward cannot hold in shared memory: torch ops on the same CUDA device,
-            # batch-chunked
+            # UMNN_B200_ALLOW_TORCH_ROUTE=1 only (the forward raised otherwise): shapes the fused backward cannot
+            # hold in shared memory go through torch ops on the same CUDA device, batch-chunked
             d_flat, d_h = _integrate_grads_chunked(x0, x, integrand, h, nb_steps, grad_output, False)
             d_h = d_h.view(h.shape)
             if not need[3]:

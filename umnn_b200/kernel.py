@@ -53,17 +53,26 @@ def flat_parameters(spec: KernelSpec) -> torch.Tensor:
 def packed_parameters(spec: KernelSpec, desc: _native.Desc, device: torch.device) -> torch.Tensor:
     """Device-side packed parameter block for this launch.
 
-    Re-packed on every call (two tiny launches) while the integrand is in training mode.  In eval
+    Re-packed on every call (a few tiny launches) while the integrand is in training mode.  In eval
     mode the block is cached ON the first Linear module (so it dies with the network) and reused
-    while every parameter keeps its storage address and autograd version -- in-place updates
-    (optimizer steps, load_state_dict, force_lipschitz) bump the version and invalidate it.
+    while (a) the library reports the same packed LAYOUT for the descriptor -- `umnn_packed_layout_id` covers the
+    resolved precision and every offset inside the block, which depend on nb_steps through the shared-memory fit,
+    so changing Q (set_steps_nb, invert with another Q) can never reuse a block in the wrong format -- and
+    (b) every parameter keeps its storage address and autograd version: in-place updates (optimizer steps,
+    load_state_dict, force_lipschitz) bump the version and invalidate it.  Updates made through `.data`
+    (p.data.copy_/mul_/clamp_) do NOT bump the version: call `invalidate_packed(integrand)` after those, or
+    keep the network in training mode.
     """
     L = _native.lib()
     owner = spec.linears[0]
     stamp = None
+    layout_id = int(L.umnn_packed_layout_id(desc))
+    if layout_id == 0:
+        msg = L.umnn_last_error()
+        raise _native.NativeError(_native_err_unsupported, msg.decode("utf-8", "replace") if msg else "")
     if not owner.training and not _repack_always:
-        stamp = (desc.precision, os.environ.get("UMNN_B200_AUTO_TC", ""), str(device)) + tuple((id(p), p.data_ptr(), p._version) for p in spec.parameters())
-        hit = owner.__dict__.get("_umnn_packed", {}).get(desc.precision)
+        stamp = (layout_id, str(device)) + tuple((id(p), p.data_ptr(), p._version) for p in spec.parameters())
+        hit = owner.__dict__.get("_umnn_packed", {}).get(layout_id)
         if hit is not None and hit[0] == stamp:
             return hit[1]
     nbytes = L.umnn_packed_params_bytes(desc)
@@ -76,10 +85,23 @@ def packed_parameters(spec: KernelSpec, desc: _native.Desc, device: torch.device
     with torch.cuda.device(device):
         _native.check(L.umnn_pack_params(desc, flat.data_ptr(), packed.data_ptr(), stream))
     if stamp is not None:
-        owner.__dict__.setdefault("_umnn_packed", {})[desc.precision] = (stamp, packed)
+        cache = owner.__dict__.setdefault("_umnn_packed", {})
+        if len(cache) >= 8:          # a sweep over many layouts must not pin device memory forever
+            cache.clear()
+        cache[layout_id] = (stamp, packed)
     else:
         owner.__dict__.pop("_umnn_packed", None)
     return packed
+
+
+def invalidate_packed(integrand) -> None:
+    """Drop the cached packed-parameter blocks of an integrand (IntegrandNetwork, IntegrandNN, ContiguousIntegrand or
+    anything with kernel_spec()).  Needed only after parameter updates that bypass autograd's version counter
+    (writes through `.data`)."""
+    get_spec = getattr(integrand, "kernel_spec", None)
+    spec = get_spec() if callable(get_spec) else None
+    if spec is not None:
+        spec.linears[0].__dict__.pop("_umnn_packed", None)
 
 
 _native_err_unsupported = -4

@@ -1,6 +1,10 @@
 """Integrand networks and the MADE conditioner (host-side mirror of the reference modules).
 
-Behavioural spec (AWehenkel/UMNN @ 59118c14), written fresh:
+Behavioural spec (AWehenkel/UMNN @ 59118c14).  IntegrandNetwork / IntegrandNN / KernelSpec are written fresh.
+MaskedLinear, MADE.update_masks / compute_ll / invert and ConditionnalMADE are NOT: they are the reference's
+out-of-scope conditioner (models/UMNN/made.py:16-192, itself derived from Karpathy's public pytorch-made),
+restated closely on purpose -- masks, degrees, state-dict keys and outputs must be identical for the reference's
+checkpoints to load and for h to be the same tensor.  Only the mask*weight caching is ours.
   * IntegrandNetwork  models/UMNN/UMNNMAF.py:235-301 -- ONE shared MLP applied to every (sample, dim)
     slot; slot (n, d) sees [x[n,d], h[n, 0*D+d], ..., h[n, (E-1)*D+d]]; LeakyReLU(0.01) hidden,
     ELU+1 or Sigmoid output.  `forward` stays a pure-torch, TorchScript-able function
@@ -92,8 +96,13 @@ class KernelSpec:
         return None
 
 
-def _sequential_spec(seq: nn.Sequential, hidden_cls, layout, n_dims):
-    """Parse Linear/act/.../Linear/out_act; returns None if the stack is not of that form."""
+def _sequential_spec(seq: nn.Sequential, hidden_cls, layout, n_dims, out_classes):
+    """Parse Linear/act/.../Linear/out_act; returns None if the stack is not of that form.
+
+    `out_classes`: the output-activation modules the CALLER's forward is consistent with.  IntegrandNetwork.forward
+    applies the Sequential as is, so only ELUPlus (ELU + 1) and Sigmoid are positive-output forms the kernel matches;
+    IntegrandNN.forward adds 1 after a plain nn.ELU.  Anything else (e.g. an IntegrandNetwork whose net was edited
+    to end in nn.ELU) is not the kernel's function -> None -> torch route."""
     mods = list(seq)
     if len(mods) < 2 or len(mods) % 2 != 0:
         return None
@@ -105,8 +114,11 @@ def _sequential_spec(seq: nn.Sequential, hidden_cls, layout, n_dims):
         if i + 1 < len(mods) - 1 and type(mods[i + 1]) is not hidden_cls:
             return None
     last = mods[-1]
+    if type(last) not in out_classes:
+        return None
     if isinstance(last, (ELUPlus, nn.ELU)):
-        if isinstance(last, nn.ELU) and last.alpha != 1.0:
+        elu = last.elu if isinstance(last, ELUPlus) else last
+        if elu.alpha != 1.0:
             return None
         out_act = _native.OUT_ELU_PLUS_1
     elif isinstance(last, nn.Sigmoid):
@@ -175,7 +187,7 @@ class IntegrandNetwork(nn.Module):
     def kernel_spec(self) -> Optional[KernelSpec]:
         if self.nout != 1:
             return None
-        return _sequential_spec(self.net, nn.LeakyReLU, _native.LAYOUT_STRIDED_D, self.nnets)
+        return _sequential_spec(self.net, nn.LeakyReLU, _native.LAYOUT_STRIDED_D, self.nnets, (ELUPlus, nn.Sigmoid))
 
 
 class ContiguousIntegrand(nn.Module):
@@ -207,7 +219,7 @@ class IntegrandNN(nn.Module):
         return self.net(torch.cat((x, h), 1)) + 1.
 
     def kernel_spec(self) -> Optional[KernelSpec]:
-        return _sequential_spec(self.net, nn.ReLU, _native.LAYOUT_CONTIG, 1)
+        return _sequential_spec(self.net, nn.ReLU, _native.LAYOUT_CONTIG, 1, (nn.ELU,))
 
 
 # --------------------------------------------------------------------------------------------------
@@ -309,6 +321,23 @@ class ConditionnalMADE(MADE):
 
     def forward(self, x, context):
         return self._strip_context(super().forward(torch.cat((context, x), 1)), x.shape[0])
+
+    def invert(self, z, context=None):
+        """Signature and the `None` return for non-Gaussian heads follow made.py:181-192.  The reference's loop body
+        reads an undefined name (`x`) and cannot run; this one solves the trailing data dimensions one by one with
+        the conditioning inputs held fixed."""
+        if context is None:
+            return super().invert(z)
+        if self.nin != self.nout / 2:
+            return None
+        # conditioning variables are the leading inputs and stay fixed; only the trailing data dims are solved for
+        u = torch.cat((context, torch.zeros(z.shape[0], self.nin_non_cond, dtype=z.dtype, device=z.device)), 1)
+        zc = torch.cat((torch.zeros_like(context), z), 1)
+        for d in range(self.cond_in, self.nin):
+            out = self.net(u)
+            mu, sigma = out[:, self.i_map[d]], out[:, self.nin + self.i_map[d]]
+            u[:, self.i_map[d]] = zc[:, self.i_map[d]] * torch.exp(sigma) + mu
+        return u[:, self.cond_in:]
 
     def computeLL(self, x, context):
         out = self._strip_context(self.net(torch.cat((context, x), 1)), x.shape[0])
