@@ -664,11 +664,15 @@ __global__ void reduce_partials_tc_kernel(const float* __restrict__ part, long l
 // ------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------
-BwdPanels bwd_panels() {
+// UMNN_B200_BWD_PANELS = auto (default) | hi | a_hilo | hilo.  auto: hi-only panels once the call fills at least one
+// whole chunk of rows (148 CTAs x kBwdMaxTiles tiles: the regime where the scratch traffic costs time), hi + lo
+// below (small calls are latency bound, the second part is free there and keeps the weight gradient at fp32 grade).
+BwdPanels bwd_panels(long long total_rows) {
     const char* e = getenv("UMNN_B200_BWD_PANELS");
     if (e && strcmp(e, "hilo") == 0) return BwdPanels{2, 2};
     if (e && strcmp(e, "a_hilo") == 0) return BwdPanels{2, 1};
-    return BwdPanels{1, 1};
+    if (e && strcmp(e, "hi") == 0) return BwdPanels{1, 1};
+    return total_rows >= 148LL * kBwdMaxTiles * kTcTile ? BwdPanels{1, 1} : BwdPanels{2, 2};
 }
 
 struct BwdTcPlan {
@@ -690,7 +694,7 @@ const char* make_bwd_plan(const umnn_desc* d, BwdTcPlan* B) {
     const bool two = tc_two_segments_public();
     if (!make_tc_layout(d, &B->F, two)) return "needs >= 2 hidden layers of width <= 254";
     if (!make_tc_dgrad_layout(d, &B->G, two)) return "input width (1 + E) above 62 or hidden width above 254";
-    B->panels = bwd_panels();
+    B->panels = bwd_panels(d->n_samples * (long long)d->n_dims * (d->nb_steps + 3));
     if (!make_tc_wgrad_plan(B->G, &B->W, B->panels)) return "weight-gradient accumulators exceed 512 TMEM columns";
     B->rps = d->nb_steps + 3;
     const TcSmem FS = make_tc_smem(B->F, B->rps, d->nb_steps);
