@@ -57,7 +57,7 @@ struct TcDgradParams {
     const uint32_t* mask[UMNN_MAX_LAYERS];     // j = 1..J
     uint8_t* dz[UMNN_MAX_LAYERS + 1];          // DZ_j panels, j = 1..J+1
     float *d_x0, *d_x, *d_h;
-    long long slot0, n_slots, slots_per_cta, row_block;
+    long long slot0, n_slots, slots_per_cta, row_block, r_pad;
     int tiles_per_cta, D, E, layout, Q, rps, out_act;
     int dz_parts;                              // parts of the dz panels: 1 = hi only, 2 = hi + lo
     const int* run_if;                         // not NULL: no-op unless *run_if != 0 (guarded bf16 re-run)
@@ -236,11 +236,11 @@ __global__ void __launch_bounds__(kThreads, 1) cc_dgrad_tc_kernel(const __grid_c
                 // dz_{J+1} panel (width 16): column 0 = dv
                 uint32_t hi, lo2;
                 split_bf16x2(dv, 0.0f, hi, lo2);
-                *reinterpret_cast<uint4*>(p.dz[J + 1] + panel_offset(pr, 0, 16, 0, p.dz_parts)) = make_uint4(hi, 0u, 0u, 0u);
-                *reinterpret_cast<uint4*>(p.dz[J + 1] + panel_offset(pr, 8, 16, 0, p.dz_parts)) = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(p.dz[J + 1] + panel_offset(pr, 0, 16, 0, p.dz_parts, p.r_pad)) = make_uint4(hi, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(p.dz[J + 1] + panel_offset(pr, 8, 16, 0, p.dz_parts, p.r_pad)) = make_uint4(0u, 0u, 0u, 0u);
                 if (p.dz_parts == 2) {
-                    *reinterpret_cast<uint4*>(p.dz[J + 1] + panel_offset(pr, 0, 16, 1, 2)) = make_uint4(lo2, 0u, 0u, 0u);
-                    *reinterpret_cast<uint4*>(p.dz[J + 1] + panel_offset(pr, 8, 16, 1, 2)) = make_uint4(0u, 0u, 0u, 0u);
+                    *reinterpret_cast<uint4*>(p.dz[J + 1] + panel_offset(pr, 0, 16, 1, 2, p.r_pad)) = make_uint4(lo2, 0u, 0u, 0u);
+                    *reinterpret_cast<uint4*>(p.dz[J + 1] + panel_offset(pr, 8, 16, 1, 2, p.r_pad)) = make_uint4(0u, 0u, 0u, 0u);
                 }
             }
             __syncwarp();
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(kThreads, 1) cc_dgrad_tc_kernel(const __grid_c
             const float dv = dvrow[bu * kTcTile + r];
             const uint32_t bits = p.mask[J][pr * 8 + pp];
             const int halves = (32 * pp + 16 < PJ) ? 2 : 1;
-            const PanelRow prow = panel_row(p.dz[J], pr, PJ, p.dz_parts);
+            const PanelRow prow = panel_row(p.dz[J], pr, PJ, p.dz_parts, p.r_pad);
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
                 if (hf < halves) {
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(kThreads, 1) cc_dgrad_tc_kernel(const __grid_c
                     tmem_ld16(taddr, v0);
                     if (two) tmem_ld16(taddr + 16, v1);
                     tmem_ld_wait();
-                    const PanelRow prow = panel_row(p.dz[jout], pr, y.npad, p.dz_parts);
+                    const PanelRow prow = panel_row(p.dz[jout], pr, y.npad, p.dz_parts, p.r_pad);
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
                         split_bf16x2(times_slope<HIDDEN_ACT>(__uint_as_float(v0[2 * i]), bits, 2 * i),
@@ -534,45 +534,72 @@ __global__ void __launch_bounds__(kWThreads, 1) cc_wgrad_tc_kernel(const __grid_
     tc_fence_after_sync();
     const uint32_t tbase = holder;
 
+    const int kbs = W.kb_per_stage;
+    const long long n_st = (n_kb + kbs - 1) / kbs;            // pipeline stages this pair walks
+
     if (warp == kWEpiWarps) {
-        // =========================================================== producer: bulk-TMA the panel tiles of a block.
-        // The <= 64 copies of one block (panel x hi/lo x k8 half) are spread over the lanes of the warp.
-        __shared__ uint32_t cp_dst[32], cp_bytes[32];
-        __shared__ unsigned long long cp_src[32], cp_blk_stride[32];
-        __shared__ uint32_t n_copies_s, total_bytes_s;
+        // =========================================================== producer: ONE bulk-TMA copy per panel and stage
+        // (this CTA's half-panel is contiguous over consecutive blocks); the copies of a stage are spread over the lanes
+        __shared__ uint32_t cp_dst[32], cp_blk_bytes[32];
+        __shared__ unsigned long long cp_src[32];
+        __shared__ uint32_t n_copies_s, blk_bytes_s;
         if (lane == 0) {
             uint32_t n = 0, bytes = 0;
             for (int pn = 0; pn < W.n_panels; ++pn) {
-                const int Wd = W.panel_width[pn], parts = W.panel_parts[pn];
                 cp_dst[n] = W.tile_off[pn];
-                cp_src[n] = (unsigned long long)(p.panel[pn] + (size_t)rank * (size_t)(16 * Wd * parts));   // this CTA's column half
-                cp_blk_stride[n] = (unsigned long long)(32 * Wd * parts);
-                cp_bytes[n] = 16u * (uint32_t)(Wd * parts);                                     // hi [+ lo], both K halves
-                bytes += cp_bytes[n];
+                cp_src[n] = (unsigned long long)(p.panel[pn] + (size_t)rank * panel_half_bytes(p.n_blocks * 16, W.panel_width[pn], W.panel_parts[pn]));
+                cp_blk_bytes[n] = W.block_bytes[pn];
+                bytes += cp_blk_bytes[n];
                 ++n;
             }
             n_copies_s = n;
-            total_bytes_s = bytes;
+            blk_bytes_s = bytes;
         }
         __syncwarp();
-        const uint32_t n_copies = n_copies_s, bytes = total_bytes_s;
-        for (long long kb = 0; kb < n_kb; ++kb) {
-            const int st = (int)(kb % kWStages);
-            if (kb >= kWStages) mbar_wait(&empty[st], (uint32_t)((kb / kWStages - 1) & 1), 400 + st);
-            if (lane == 0) mbar_expect_tx(&full[st], bytes);
+        const uint32_t n_copies = n_copies_s, blk_bytes = blk_bytes_s;
+        for (long long si = 0; si < n_st; ++si) {
+            const int st = (int)(si % kWStages);
+            if (si >= kWStages) mbar_wait(&empty[st], (uint32_t)((si / kWStages - 1) & 1), 400 + st);
+            const long long kb0 = si * kbs;
+            const uint32_t nb = (uint32_t)((n_kb - kb0 < kbs) ? (n_kb - kb0) : kbs);     // blocks in this stage (tail: fewer)
+            if (lane == 0) mbar_expect_tx(&full[st], nb * blk_bytes);
             __syncwarp();
             uint8_t* sb = smem + (size_t)st * W.stage_bytes;
-            const unsigned long long blk = (unsigned long long)(blk_begin + kb);
+            const unsigned long long blk = (unsigned long long)(blk_begin + kb0);
             for (uint32_t i = lane; i < n_copies; i += 32)
-                bulk_g2s(sb + cp_dst[i], reinterpret_cast<const uint8_t*>(cp_src[i] + blk * cp_blk_stride[i]), cp_bytes[i], &full[st]);
+                bulk_g2s(sb + cp_dst[i], reinterpret_cast<const uint8_t*>(cp_src[i] + blk * cp_blk_bytes[i]), nb * cp_blk_bytes[i], &full[st]);
         }
         __syncwarp();
     } else if (warp == kWEpiWarps + 1) {
         // =========================================================== MMA issuer
+        // Per layer the four operand descriptors of (stage 0, block 0) are built once; a later stage / block only adds
+        // its byte offset (>> 4) to the descriptor's address field (shared-memory addresses stay below 2^18, so the
+        // 14-bit field never carries).
+        __shared__ unsigned long long d_ahi[UMNN_MAX_LAYERS], d_alo[UMNN_MAX_LAYERS], d_bhi[UMNN_MAX_LAYERS], d_blo[UMNN_MAX_LAYERS];
+        __shared__ uint32_t d_idesc[UMNN_MAX_LAYERS], d_mstep[UMNN_MAX_LAYERS], d_nstep[UMNN_MAX_LAYERS], d_flags[UMNN_MAX_LAYERS];
         const uint32_t sbase = smem_u32(smem);
-        for (long long kb = 0; kb < n_kb; ++kb) {
-            const int st = (int)(kb % kWStages);
-            const uint32_t ph = (uint32_t)((kb / kWStages) & 1);
+        if (lane == 0) {
+            for (int l = 0; l < W.n_layers; ++l) {
+                const TcWgradLayer& y = W.layer[l];
+                // tiles hold [block][hi | lo] x [k8][W/16 core matrices]; the M tile is read 128 rows deep although only
+                // W/2 are staged (rows beyond feed accumulator rows nobody reads)
+                const uint32_t lbo_m = (uint32_t)(y.m_width / 16) * 128u, lbo_n = (uint32_t)(y.n_width / 16) * 128u;
+                d_ahi[l] = make_smem_desc(sbase + W.tile_off[y.m_panel], lbo_m, 128);
+                d_alo[l] = make_smem_desc(sbase + W.tile_off[y.m_panel] + 16u * y.m_width, lbo_m, 128);
+                d_bhi[l] = make_smem_desc(sbase + W.tile_off[y.n_panel], lbo_n, 128);
+                d_blo[l] = make_smem_desc(sbase + W.tile_off[y.n_panel] + 16u * y.n_width, lbo_n, 128);
+                d_idesc[l] = make_idesc_bf16_f32(256, y.n_width) | (1u << 15) | (1u << 16);
+                d_mstep[l] = W.block_bytes[y.m_panel] >> 4;
+                d_nstep[l] = W.block_bytes[y.n_panel] >> 4;
+                // hi*hi always; the cross terms only for operands whose panel carries a lo part
+                d_flags[l] = (W.panel_parts[y.m_panel] == 2 ? 1u : 0u) | (W.panel_parts[y.n_panel] == 2 ? 2u : 0u);
+            }
+        }
+        __syncwarp();
+        const int n_layers = W.n_layers;
+        for (long long si = 0; si < n_st; ++si) {
+            const int st = (int)(si % kWStages);
+            const uint32_t ph = (uint32_t)((si / kWStages) & 1);
             mbar_wait(&full[st], ph, 410 + st);
             // both CTAs' tiles of this stage must have landed before the pair-wide MMA reads them
             if (elect_one_sync()) mbar_arrive_cluster(&peer_ready[st], 0);
@@ -580,29 +607,25 @@ __global__ void __launch_bounds__(kWThreads, 1) cc_wgrad_tc_kernel(const __grid_
             if (rank == 0) {
                 mbar_wait(&peer_ready[st], ph, 420 + st);
                 tc_fence_after_sync();
-                const uint32_t stage_addr = sbase + (uint32_t)st * W.stage_bytes;
-                for (int l = 0; l < W.n_layers; ++l) {
-                    const TcWgradLayer& y = W.layer[l];
-                    const uint32_t idesc = make_idesc_bf16_f32(256, y.n_width) | (1u << 15) | (1u << 16);
-                    // tiles hold [hi | lo] x [k8][W/16 core matrices]; the M tile is read 128 rows deep although only
-                    // W/2 are staged (rows beyond feed accumulator rows nobody reads)
-                    const uint32_t lbo_m = (uint32_t)(y.m_width / 16) * 128u, lbo_n = (uint32_t)(y.n_width / 16) * 128u;
-                    const uint64_t a_hi = make_smem_desc(stage_addr + W.tile_off[y.m_panel], lbo_m, 128);
-                    const uint64_t a_lo = make_smem_desc(stage_addr + W.tile_off[y.m_panel] + 16u * y.m_width, lbo_m, 128);
-                    const uint64_t b_hi = make_smem_desc(stage_addr + W.tile_off[y.n_panel], lbo_n, 128);
-                    const uint64_t b_lo = make_smem_desc(stage_addr + W.tile_off[y.n_panel] + 16u * y.n_width, lbo_n, 128);
-                    const uint32_t d_addr = tbase + (uint32_t)y.tmem_col;
-                    // hi*hi always; the cross terms only for operands whose panel carries a lo part
-                    const bool m_lo = W.panel_parts[y.m_panel] == 2, n_lo = W.panel_parts[y.n_panel] == 2;
-                    if (elect_one_sync()) {
-                        mma_ss<2>(d_addr, a_hi, b_hi, idesc, kb > 0);
-                        if (m_lo) mma_ss<2>(d_addr, a_lo, b_hi, idesc, 1);
-                        if (n_lo) mma_ss<2>(d_addr, a_hi, b_lo, idesc, 1);
+                const long long kb0 = si * kbs;
+                const int nb = (int)((n_kb - kb0 < kbs) ? (n_kb - kb0) : kbs);
+                const unsigned long long st_off = (unsigned long long)(((uint32_t)st * W.stage_bytes) >> 4);
+                if (elect_one_sync()) {
+                    for (int l = 0; l < n_layers; ++l) {
+                        const uint32_t idesc = d_idesc[l], fl = d_flags[l];
+                        const uint32_t d_addr = tbase + (uint32_t)W.layer[l].tmem_col;
+                        unsigned long long ahi = d_ahi[l] + st_off, alo = d_alo[l] + st_off, bhi = d_bhi[l] + st_off, blo = d_blo[l] + st_off;
+                        const unsigned long long ms = d_mstep[l], ns = d_nstep[l];
+                        for (int i = 0; i < nb; ++i) {
+                            mma_ss<2>(d_addr, ahi, bhi, idesc, (si > 0 || i > 0) ? 1u : 0u);
+                            if (fl & 1u) mma_ss<2>(d_addr, alo, bhi, idesc, 1);
+                            if (fl & 2u) mma_ss<2>(d_addr, ahi, blo, idesc, 1);
+                            ahi += ms; alo += ms; bhi += ns; blo += ns;
+                        }
                     }
-                    __syncwarp();
+                    // release the stage in BOTH CTAs once these MMAs have read it
+                    mma_commit<2>(&empty[st], 0x3);
                 }
-                // release the stage in BOTH CTAs once these MMAs have read it
-                if (elect_one_sync()) mma_commit<2>(&empty[st], 0x3);
                 __syncwarp();
             }
         }
@@ -701,9 +724,22 @@ const char* make_bwd_plan(const umnn_desc* d, BwdTcPlan* B) {
     if (FS.total > kTcMaxSmem) return "forward weights + per-tile context do not fit in 227 KB of shared memory";
     B->GS = make_tc_dgrad_smem(B->G, d->n_ctx, d->nb_steps);
     if (B->GS.total > kTcMaxSmem) return "transposed weights do not fit in 227 KB of shared memory";
-    B->w_stages = (int)((kTcMaxSmem - 2048) / B->W.stage_bytes);
-    if (B->w_stages > kWMaxStages) B->w_stages = kWMaxStages;
-    if (B->w_stages < 2) return "weight-gradient stages do not fit in 227 KB of shared memory";
+    // pass W pipeline: as many 16-row blocks per stage (<= 4) as still leave >= 3 stages in shared memory
+    // (UMNN_B200_WGRAD_KBS = 1..4 pins the count: A/B measurements)
+    {
+        int forced = 0;
+        if (const char* e = getenv("UMNN_B200_WGRAD_KBS")) forced = atoi(e);
+        int best = 0;
+        for (int kbs = 4; kbs >= 1; --kbs) {
+            if (forced >= 1 && forced <= 4 && kbs != forced) continue;
+            tc_wgrad_set_stage(&B->W, kbs);
+            const int stages = (int)((kTcMaxSmem - 2048) / B->W.stage_bytes);
+            if (stages >= 3 || (kbs == 1 && stages >= 2) || (forced == kbs && stages >= 2)) { best = kbs; break; }
+        }
+        if (!best) return "weight-gradient stages do not fit in 227 KB of shared memory";
+        B->w_stages = (int)((kTcMaxSmem - 2048) / B->W.stage_bytes);
+        if (B->w_stages > kWMaxStages) B->w_stages = kWMaxStages;
+    }
     B->w_smem = (size_t)B->W.stage_bytes * B->w_stages + 1024;
     B->P = 0;
     for (int l = 0; l < d->n_layers; ++l) B->P += (long long)d->widths[l] * d->widths[l + 1] + d->widths[l + 1];
@@ -815,6 +851,7 @@ int launch_backward_tc(const umnn_desc* d, const float* x0, const float* x, cons
     emit.v = reinterpret_cast<float*>(ws + B.off_v);
     emit.row_block = B.row_block;
     emit.parts = B.panels.a_parts;
+    emit.r_pad = B.R_pad;
 
     TcDgradParams g{};
     g.x0 = x0; g.x = x; g.weights = weights; g.grad_out = grad_out; g.grad_fx = grad_fx;
@@ -828,6 +865,7 @@ int launch_backward_tc(const umnn_desc* d, const float* x0, const float* x, cons
     g.D = d->n_dims; g.E = d->n_ctx; g.layout = d->layout; g.Q = d->nb_steps; g.rps = B.rps; g.out_act = d->out_act;
     g.L = B.G; g.S = B.GS;
     g.dz_parts = B.panels.dz_parts;
+    g.r_pad = B.R_pad;
 
     TcWgradParams w{};
     for (int pn = 0; pn < B.W.n_panels; ++pn) w.panel[pn] = ws + B.off_panel[pn];

@@ -351,9 +351,9 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
                         }
                         split_bf16x2(v2[0], v2[1], hi4[i], lo4[i]);
                     }
-                    *reinterpret_cast<uint4*>(p.emit.a[0] + panel_offset(pr, gidx * 8, W0, 0, kParts)) = make_uint4(hi4[0], hi4[1], hi4[2], hi4[3]);
+                    *reinterpret_cast<uint4*>(p.emit.a[0] + panel_offset(pr, gidx * 8, W0, 0, kParts, p.emit.r_pad)) = make_uint4(hi4[0], hi4[1], hi4[2], hi4[3]);
                     if constexpr (EMIT == 2)
-                        *reinterpret_cast<uint4*>(p.emit.a[0] + panel_offset(pr, gidx * 8, W0, 1, kParts)) = make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]);
+                        *reinterpret_cast<uint4*>(p.emit.a[0] + panel_offset(pr, gidx * 8, W0, 1, kParts, p.emit.r_pad)) = make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]);
                 }
             }
             float* cv = cvec + (size_t)b * p.S.max_slots * L.npad1;
@@ -412,7 +412,7 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
             }
             tmem_st16(tbase + lane_sel + kColQ + 16u * c16, o);
             if (EMIT) {
-                emit16<kParts>(panel_row(p.emit.a[1], cta_row0 + (long long)tile * kTcTile + r, L.npad1, kParts), 16 * c16, ob);
+                emit16<kParts>(panel_row(p.emit.a[1], cta_row0 + (long long)tile * kTcTile + r, L.npad1, kParts, p.emit.r_pad), 16 * c16, ob);
                 return sign_mask16(pre);
             }
             return 0u;
@@ -459,7 +459,7 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
                     const long long pr = cta_row0 + (long long)t * kTcTile + r;
                     PanelRow prow;
                     if (EMIT) {
-                        prow = panel_row(p.emit.a[m + 2], pr, y.npad, kParts);
+                        prow = panel_row(p.emit.a[m + 2], pr, y.npad, kParts, p.emit.r_pad);
                         // signs first: the accumulator registers die as they are converted below
                         p.emit.mask[m + 2][pr * 8 + pp] = sign_mask16(v0) | (two ? sign_mask16(v1) << 4 : 0u);
                     }
@@ -523,7 +523,7 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
                     if (EMIT) {
                         // last hidden activations a_J (operand of the output layer's weight gradient) and their signs
                         const long long pr = cta_row0 + (long long)t * kTcTile + r;
-                        const PanelRow prow = panel_row(p.emit.a[n_mma + 1], pr, L.npadL, kParts);
+                        const PanelRow prow = panel_row(p.emit.a[n_mma + 1], pr, L.npadL, kParts, p.emit.r_pad);
                         uint32_t o[16];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {

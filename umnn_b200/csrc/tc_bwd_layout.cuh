@@ -10,11 +10,11 @@
 //
 // A panel of width W stores, for R_pad rows in blocks of 16 rows, `parts` bf16 values per element: the rounded value
 // ("hi", parts = 1) or hi AND the residual lo (parts = 2).  In pass W every panel is one operand of one cta_group::2
-// MMA, whose two CTAs each supply half of the columns, so a block is laid out as
-//   [column half (2)][part (parts)][k8 = (row % 16) / 8][col8][row % 8][col % 8]:
-// each CTA fetches its half of a block (parts * 32 * W/2 bytes, contiguous) with ONE bulk-TMA copy and the result is
-// directly `parts` MN-major UMMA operand tiles (128-byte core matrices; LBO = (W/16)*128 between the K halves,
-// SBO = 128).
+// MMA, whose two CTAs each supply half of the columns, so a panel is two half-panels (one per CTA of the pair), each
+//   [16-row block][part (parts)][k8 = (row % 16) / 8][col8][row % 8][col % 8]:
+// a CTA fetches its half of SEVERAL consecutive blocks (one pipeline stage of pass W) with ONE contiguous bulk-TMA
+// copy and every block of it is directly `parts` MN-major UMMA operand tiles (128-byte core matrices;
+// LBO = (W/16)*128 between the K halves, SBO = 128).
 //
 // Which panels carry a lo part is the backward's HBM-traffic / precision trade (BwdPanels below).  The panels only
 // feed the WEIGHT gradient dW = sum over rows of dz^T a: per-row rounding errors of a bf16 operand (2^-9 relative,
@@ -30,11 +30,14 @@ namespace umnn {
 constexpr int kBwdMaxHidden = UMNN_MAX_LAYERS - 1;          // J <= 7
 constexpr int kBwdMaxTiles = 32;                            // tiles of 128 rows per CTA and chunk
 
-__host__ __device__ inline size_t panel_offset(long long pr, int c, int W, int part, int parts) {
+// bytes of one half-panel: r_pad rows (a multiple of 16) x W/2 columns x parts x 2 bytes
+__host__ __device__ inline size_t panel_half_bytes(long long r_pad, int W, int parts) { return (size_t)r_pad * (size_t)(W * parts); }
+
+__host__ __device__ inline size_t panel_offset(long long pr, int c, int W, int part, int parts, long long r_pad) {
     const int hw = W >> 1;                       // columns per CTA half (multiple of 8)
     const int half = c >= hw ? 1 : 0;
     const int cin = c - half * hw;
-    return (size_t)(pr >> 4) * (size_t)(32 * W * parts) + (size_t)half * (size_t)(32 * hw * parts) + (size_t)part * (size_t)(32 * hw) +
+    return (size_t)half * panel_half_bytes(r_pad, W, parts) + (size_t)(pr >> 4) * (size_t)(32 * hw * parts) + (size_t)part * (size_t)(32 * hw) +
            (size_t)(((pr >> 3) & 1) * (hw >> 3) + (cin >> 3)) * 128 + (size_t)(pr & 7) * 16 + (size_t)(cin & 7) * 2;
 }
 
@@ -43,15 +46,15 @@ __host__ __device__ inline size_t panel_offset(long long pr, int c, int W, int p
 struct PanelRow {
     uint8_t* base;
     uint32_t hw;           // columns per CTA half
-    uint32_t half_off;     // extra offset of the second column half (32*hw*parts - 16*hw)
+    uint32_t half_off;     // extra offset of the second column half (half-panel bytes - 16*hw; < 4 GiB by the plan)
     uint32_t lo_off;       // offset of the lo part (parts == 2)
 };
-__host__ __device__ inline PanelRow panel_row(uint8_t* panel, long long pr, int W, int parts) {
+__host__ __device__ inline PanelRow panel_row(uint8_t* panel, long long pr, int W, int parts, long long r_pad) {
     PanelRow R;
     const uint32_t hw = (uint32_t)W >> 1;
-    R.base = panel + (size_t)(pr >> 4) * (size_t)(32 * W * parts) + (size_t)(((uint32_t)(pr >> 3) & 1u) * hw * 16u + ((uint32_t)pr & 7u) * 16u);
+    R.base = panel + (size_t)(pr >> 4) * (size_t)(32 * hw * parts) + (size_t)(((uint32_t)(pr >> 3) & 1u) * hw * 16u + ((uint32_t)pr & 7u) * 16u);
     R.hw = hw;
-    R.half_off = 32u * hw * (uint32_t)parts - 16u * hw;
+    R.half_off = (uint32_t)(panel_half_bytes(r_pad, W, parts) - 16u * hw);
     R.lo_off = 32u * hw;
     return R;
 }
@@ -180,10 +183,27 @@ struct TcWgradPlan {
     int n_panels;               // panel table: A_0..A_J then DZ_1..DZ_{J+1}
     int panel_width[2 * UMNN_MAX_LAYERS + 2];
     int panel_parts[2 * UMNN_MAX_LAYERS + 2];
-    uint32_t stage_bytes;       // bytes staged per 16-row K block and CTA (+ slack for the M-tile over-read)
-    uint32_t tile_off[2 * UMNN_MAX_LAYERS + 2];      // smem offset of the panel's tile (hi, then lo) inside a stage
+    int kb_per_stage;           // 16-row K blocks per pipeline stage (1..4), see tc_wgrad_set_stage
+    uint32_t block_bytes[2 * UMNN_MAX_LAYERS + 2];   // bytes of one 16-row block of a CTA's half-panel (16 * W * parts)
+    uint32_t stage_bytes;       // bytes staged per stage and CTA (+ slack for the M-tile over-read)
+    uint32_t tile_off[2 * UMNN_MAX_LAYERS + 2];      // smem offset of the panel's blocks ([block][part]...) inside a stage
     int tmem_cols_used;
 };
+
+// A pipeline stage of pass W holds `kbs` consecutive 16-row blocks of every panel (one bulk-TMA copy per panel and
+// stage).  More blocks per stage = fewer barrier round trips and copy requests per row: with one block per stage the
+// MMA issuer's per-stage bookkeeping (~1 us) was the bound, not HBM or the tensor pipe (profiles/r2_bwd_passes.md).
+inline void tc_wgrad_set_stage(TcWgradPlan* W, int kbs) {
+    W->kb_per_stage = kbs;
+    uint32_t off = 0;
+    for (int p = 0; p < W->n_panels; ++p) {
+        W->tile_off[p] = off;
+        off += (uint32_t)kbs * W->block_bytes[p];
+    }
+    // an M tile is read as 128 rows per K half although only W/2 are staged: the tensor core over-reads up to
+    // (128 - 8) * 16 bytes past the last K half of the last block -> keep that much slack inside the stage
+    W->stage_bytes = off + 2048;
+}
 
 // panel indices
 inline int panel_A(int j) { return j; }                             // j = 0..J
@@ -220,14 +240,9 @@ inline bool make_tc_wgrad_plan(const TcDgradLayout& G, TcWgradPlan* W, BwdPanels
     }
     W->tmem_cols_used = col;
     if (col > 512) return false;
-    uint32_t off = 0;
-    for (int p = 0; p < W->n_panels; ++p) {
-        W->tile_off[p] = off;
-        off += 16u * (uint32_t)W->panel_width[p] * (uint32_t)W->panel_parts[p];   // `parts` tiles of half the columns, 16 rows
-    }
-    // an M tile is read as 128 rows per K half although only W/2 are staged: the tensor core over-reads up to
-    // (128 - 8) * 16 bytes past the last K half of the last tile -> keep that much slack inside the stage
-    W->stage_bytes = off + 2048;
+    for (int p = 0; p < W->n_panels; ++p)
+        W->block_bytes[p] = 16u * (uint32_t)W->panel_width[p] * (uint32_t)W->panel_parts[p];   // `parts` tiles of half the columns
+    tc_wgrad_set_stage(W, 1);
     return true;
 }
 

@@ -14,6 +14,7 @@ struct TcEmit {
     int width[UMNN_MAX_LAYERS];        // panel widths P_j
     long long row_block;               // padded rows per CTA (tiles_per_cta * 128)
     int parts;                         // 1: hi only, 2: hi + lo
+    long long r_pad;                   // padded rows of the chunk's panels (n_cta * row_block)
 };
 
 struct TcParams {

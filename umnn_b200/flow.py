@@ -52,6 +52,16 @@ class EmbeddingNetwork(nn.Module):
         self.m_embeding = self.made.forward(x_made, context)
         return self.m_embeding
 
+    def embedding_of_dim(self, x_made, j, context=None):
+        """make_embeding(x_made, context)[:, j::in_d] -- the E context values of dimension j ([B, E]; column 0 is the
+        offset z0 of UMNNMAF.py:203) -- from the conditioner's hidden layers plus E rows of its last masked layer
+        instead of all E*in_d of them."""
+        if isinstance(self.made, ConditionnalMADE):
+            hid = self.made.hidden_forward(x_made, context)
+        else:
+            hid = self.made.hidden_forward(x_made)
+        return self.made.output_columns(hid, j, self.in_d)
+
     def forward(self, x_t):
         return self.parallel_nets.forward(x_t, self.m_embeding)
 
@@ -265,9 +275,9 @@ class UMNNMAF(nn.Module):
                 kernel.invert_bracket_step(integ.view(n_grid, B), xa, grid, offset, scale, target, left, right, xb, x_mid)
                 xa, xb = xb, xa
 
-        def load(j, h_all):
-            h_j.view(n_grid, B, E).copy_(h_all[:, j::D].unsqueeze(0).expand(n_grid, -1, -1))
-            offset.copy_(h_all[:, j])
+        def load(j, h_cols):
+            h_j.view(n_grid, B, E).copy_(h_cols.unsqueeze(0).expand(n_grid, -1, -1))
+            offset.copy_(h_cols[:, 0])
             target.copy_(z[:, j])
             scale.copy_(s[j:j + 1])
             left.fill_(-50.)
@@ -280,8 +290,8 @@ class UMNNMAF(nn.Module):
             for j in range(self.input_size):
                 if j % 100 == 0:
                     print(j)
-                h_all = self.net.make_embeding(x_inv, context).float()
-                load(j, h_all)
+                # only the E conditioner outputs dimension j reads (the reference runs the full MADE, UMNNMAF.py:199)
+                load(j, self.net.embedding_of_dim(x_inv, j, context).float())
                 if use_graph and graph is None:
                     # first dimension: run eagerly on a side stream (loads the tables, packs the parameters, sizes the
                     # allocator pools), then capture; the eager results are the first dimension's.  The graph lives

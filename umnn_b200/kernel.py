@@ -47,7 +47,7 @@ def repack_every_call():
 
 
 def flat_parameters(spec: KernelSpec) -> torch.Tensor:
-    return torch.cat([p.detach().reshape(-1) for p in spec.parameters()])
+    return torch.cat([p.detach().reshape(-1) for p in spec.param_list])
 
 
 def packed_parameters(spec: KernelSpec, desc: _native.Desc, device: torch.device) -> torch.Tensor:
@@ -66,12 +66,12 @@ def packed_parameters(spec: KernelSpec, desc: _native.Desc, device: torch.device
     L = _native.lib()
     owner = spec.linears[0]
     stamp = None
-    layout_id = int(L.umnn_packed_layout_id(desc))
+    layout_id = _desc_info(spec, desc, "layout")
     if layout_id == 0:
         msg = L.umnn_last_error()
         raise _native.NativeError(_native_err_unsupported, msg.decode("utf-8", "replace") if msg else "")
     if not owner.training and not _repack_always:
-        stamp = (layout_id, str(device)) + tuple((id(p), p.data_ptr(), p._version) for p in spec.parameters())
+        stamp = (layout_id, device.index, *[v for p in spec.param_list for v in (p.data_ptr(), p._version)])
         hit = owner.__dict__.get("_umnn_packed", {}).get(layout_id)
         if hit is not None and hit[0] == stamp:
             return hit[1]
@@ -108,13 +108,72 @@ _native_err_unsupported = -4
 
 
 def make_desc(spec: KernelSpec, x: torch.Tensor, nb_steps: int, precision: Optional[int] = None) -> _native.Desc:
+    """Descriptor of this launch.  Descriptors (and what the library derives from them on the host: packed layout id,
+    workspace sizes) are memoised on the KernelSpec, which the integrand modules cache in turn: a small-batch call
+    must not spend more time describing the launch than the GPU spends running it."""
     B, Dx = x.shape
+    prec = default_precision() if precision is None else precision
+    key = (B, Dx, int(nb_steps), prec)
+    hit = spec.desc_cache.get(key)
+    if hit is not None:
+        return hit
     if spec.layout == _native.LAYOUT_STRIDED_D and Dx != spec.n_dims:
         raise ValueError(f"x has {Dx} columns but the integrand network was built for {spec.n_dims}")
     if spec.layout == _native.LAYOUT_CONTIG and Dx != 1:
         raise ValueError(f"contiguous-context integrands integrate a single variable (x is [B, 1]); got [B, {Dx}]")
-    return _native.make_desc(spec.layout, B, Dx, spec.n_ctx, spec.widths, spec.hidden_act, spec.out_act,
-                             int(nb_steps), default_precision() if precision is None else precision)
+    d = _native.make_desc(spec.layout, B, Dx, spec.n_ctx, spec.widths, spec.hidden_act, spec.out_act, int(nb_steps), prec)
+    d._umnn_key = key
+    if len(spec.desc_cache) > 64:
+        spec.desc_cache.clear()
+    spec.desc_cache[key] = d
+    return d
+
+
+def _desc_info(spec: KernelSpec, desc: _native.Desc, what: str):
+    """Host-side facts the library derives from a descriptor, memoised per descriptor object: 'layout' (packed layout
+    id), 'ws0' / 'ws1' (forward / backward workspace bytes).  They depend on the descriptor and on process-wide
+    environment switches read at call time (UMNN_B200_TC_SEGMENTS, UMNN_B200_BWD_PANELS), so the memo is keyed on
+    those too."""
+    L = _native.lib()
+    dkey = getattr(desc, "_umnn_key", None)
+    if dkey is None:        # a descriptor built elsewhere: ask the library directly
+        return int(L.umnn_packed_layout_id(desc)) if what == "layout" else int(L.umnn_workspace_bytes(desc, 0 if what == "ws0" else 1))
+    env = (os.environ.get("UMNN_B200_TC_SEGMENTS"), os.environ.get("UMNN_B200_BWD_PANELS"), os.environ.get("UMNN_B200_TC_NARROW"))
+    key = (dkey, what, env)
+    hit = spec.info_cache.get(key)
+    if hit is not None:
+        return hit
+    if what == "layout":
+        v = int(L.umnn_packed_layout_id(desc))
+    elif what == "ws0":
+        v = int(L.umnn_workspace_bytes(desc, 0))
+    else:
+        v = int(L.umnn_workspace_bytes(desc, 1))
+    if len(spec.info_cache) > 256:
+        spec.info_cache.clear()
+    spec.info_cache[key] = v
+    return v
+
+
+_flag_ws = {}
+
+
+def _forward_workspace(nbytes: int, dev: torch.device, stream: int) -> Optional[torch.Tensor]:
+    """The forward's 256-byte workspace (the overflow flag of a guarded FP16X3 call), one persistent buffer per
+    (device, stream): calls on one stream are ordered, so they can share it, and a small-batch call saves an
+    allocation.  Buffers handed out while a CUDA graph is being captured come from the capture's own pool."""
+    if nbytes == 0:
+        return None
+    if torch.cuda.is_current_stream_capturing():
+        return torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    key = (dev.index, stream)
+    buf = _flag_ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        if len(_flag_ws) > 64:
+            _flag_ws.clear()
+        buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
+        _flag_ws[key] = buf
+    return buf
 
 
 def cc_forward(spec: KernelSpec, x0: Optional[torch.Tensor], x: torch.Tensor, h: torch.Tensor, nb_steps: int,
@@ -147,13 +206,18 @@ def cc_forward(spec: KernelSpec, x0: Optional[torch.Tensor], x: torch.Tensor, h:
         return out, fx, fx0
     packed = packed_parameters(spec, desc, dev)
     w, t = device_tables(nb_steps, dev)
-    ws_bytes = L.umnn_workspace_bytes(desc, 0)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
+    ws_bytes = _desc_info(spec, desc, "ws0")
     stream = torch.cuda.current_stream(dev).cuda_stream
-    with torch.cuda.device(dev):
-        _native.check(L.umnn_cc_forward(desc, _ptr(x0), x.data_ptr(), h.data_ptr(), packed.data_ptr(),
-                                        t.data_ptr(), w.data_ptr(), out.data_ptr(), _ptr(fx), _ptr(fx0),
-                                        _ptr(ws), ws_bytes, stream))
+    ws = _forward_workspace(ws_bytes, dev, stream)
+    args = (desc, _ptr(x0), x.data_ptr(), h.data_ptr(), packed.data_ptr(), t.data_ptr(), w.data_ptr(), out.data_ptr(),
+            _ptr(fx), _ptr(fx0), _ptr(ws), ws_bytes, stream)
+    if torch.cuda.current_device() == dev.index:
+        rc = L.umnn_cc_forward(*args)
+    else:
+        with torch.cuda.device(dev):
+            rc = L.umnn_cc_forward(*args)
+    if rc != 0:
+        _native.check(rc)
     return out, fx, fx0
 
 
@@ -202,9 +266,8 @@ def backward_precision(spec: KernelSpec, x: torch.Tensor, nb_steps: int) -> Opti
         cands = [default_precision(), _native.PREC_FP32]
     if x.shape[0] == 0:
         return cands[-1]
-    L = _native.lib()
     for prec in cands:
-        if L.umnn_workspace_bytes(make_desc(spec, x, nb_steps, prec), 1) > 0:
+        if _desc_info(spec, make_desc(spec, x, nb_steps, prec), "ws1") > 0:
             return prec
     return None
 
@@ -245,8 +308,9 @@ def cc_backward(spec: KernelSpec, x0: Optional[torch.Tensor], x: torch.Tensor, h
         return d_x0, d_x, d_flat, d_h
     packed = packed_parameters(spec, desc, dev)
     w, t = device_tables(nb_steps, dev)
-    ws_bytes = L.umnn_workspace_bytes(desc, 1)
+    ws_bytes = _desc_info(spec, desc, "ws1")
     if ws_bytes == 0:
+        L.umnn_workspace_bytes(desc, 1)          # refresh the thread-local error string
         msg = L.umnn_last_error()
         raise _native.NativeError(_native_err_unsupported, msg.decode("utf-8", "replace") if msg else "")
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)

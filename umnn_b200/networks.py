@@ -68,20 +68,21 @@ def _mlp(sizes: List[int], hidden: type, linear=nn.Linear) -> List[nn.Module]:
 
 class KernelSpec:
     """What the fused kernel needs to know about a recognised integrand."""
-    __slots__ = ("layout", "widths", "hidden_act", "out_act", "linears", "n_dims")
+    __slots__ = ("layout", "widths", "hidden_act", "out_act", "linears", "n_dims", "desc_cache", "info_cache", "param_list")
 
     def __init__(self, layout, widths, hidden_act, out_act, linears, n_dims):
         self.layout, self.widths, self.hidden_act, self.out_act = layout, widths, hidden_act, out_act
         self.linears, self.n_dims = linears, n_dims
+        self.desc_cache, self.info_cache = {}, {}     # launch descriptors and what the library derives from them
+        # the Parameter objects at the time the spec was built (the spec cache is keyed on their identities)
+        self.param_list = [t for lin in linears for t in (lin.weight, lin.bias)]
 
     @property
     def n_ctx(self):
         return self.widths[0] - 1
 
     def parameters(self):
-        for lin in self.linears:
-            yield lin.weight
-            yield lin.bias
+        return iter(self.param_list)
 
     def supported(self) -> Optional[str]:
         """None if the kernel can serve this shape, else the reason."""
@@ -94,6 +95,19 @@ class KernelSpec:
         if self.widths[-1] != 1:
             return "output width must be 1"
         return None
+
+
+def _cached_spec(owner: nn.Module, seq: nn.Sequential, build):
+    """KernelSpec of `seq`, rebuilt only when the Sequential's module list (or an activation's slope / alpha) changes:
+    parsing the stack on every call costs more than a small launch."""
+    key = tuple([(id(m), m.__dict__.get("negative_slope"), m.__dict__.get("alpha"), *map(id, m._parameters.values()))
+                 for m in seq._modules.values()])
+    hit = owner.__dict__.get("_umnn_spec")
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    spec = build()
+    owner.__dict__["_umnn_spec"] = (key, spec)
+    return spec
 
 
 def _sequential_spec(seq: nn.Sequential, hidden_cls, layout, n_dims, out_classes):
@@ -187,7 +201,8 @@ class IntegrandNetwork(nn.Module):
     def kernel_spec(self) -> Optional[KernelSpec]:
         if self.nout != 1:
             return None
-        return _sequential_spec(self.net, nn.LeakyReLU, _native.LAYOUT_STRIDED_D, self.nnets, (ELUPlus, nn.Sigmoid))
+        return _cached_spec(self, self.net, lambda: _sequential_spec(self.net, nn.LeakyReLU, _native.LAYOUT_STRIDED_D,
+                                                                     self.nnets, (ELUPlus, nn.Sigmoid)))
 
 
 class ContiguousIntegrand(nn.Module):
@@ -205,7 +220,11 @@ class ContiguousIntegrand(nn.Module):
         spec = self.parallel_nets.kernel_spec()
         if spec is None:
             return None
-        return KernelSpec(_native.LAYOUT_CONTIG, spec.widths, spec.hidden_act, spec.out_act, spec.linears, 1)
+        hit = self.__dict__.get("_umnn_contig")
+        if hit is None or hit[0] is not spec:
+            hit = (spec, KernelSpec(_native.LAYOUT_CONTIG, spec.widths, spec.hidden_act, spec.out_act, spec.linears, 1))
+            self.__dict__["_umnn_contig"] = hit
+        return hit[1]
 
 
 class IntegrandNN(nn.Module):
@@ -219,7 +238,7 @@ class IntegrandNN(nn.Module):
         return self.net(torch.cat((x, h), 1)) + 1.
 
     def kernel_spec(self) -> Optional[KernelSpec]:
-        return _sequential_spec(self.net, nn.ReLU, _native.LAYOUT_CONTIG, 1, (nn.ELU,))
+        return _cached_spec(self, self.net, lambda: _sequential_spec(self.net, nn.ReLU, _native.LAYOUT_CONTIG, 1, (nn.ELU,)))
 
 
 # --------------------------------------------------------------------------------------------------
@@ -234,9 +253,24 @@ class MaskedLinear(nn.Linear):
 
     def set_mask(self, mask):
         self.mask.data.copy_(torch.from_numpy(mask.astype(np.uint8).T))
+        self.__dict__.pop("_masked_cache", None)
+
+    def masked_weight(self):
+        """mask * weight (made.py:26-27 recomputes it on every forward).  When no gradient can flow into the weight
+        (no_grad / eval inference, sampling) the product is cached and reused until the weight or the mask changes
+        (storage address + autograd version, as for the packed integrand parameters); with autograd on it is computed
+        in the graph as in the reference."""
+        if torch.is_grad_enabled() and self.weight.requires_grad:
+            return self.mask * self.weight
+        stamp = (self.weight.data_ptr(), self.weight._version, self.mask.data_ptr(), self.mask._version, self.weight.device)
+        hit = self.__dict__.get("_masked_cache")
+        if hit is None or hit[0] != stamp:
+            hit = (stamp, (self.mask * self.weight).detach())
+            self.__dict__["_masked_cache"] = hit
+        return hit[1]
 
     def forward(self, input):
-        return F.linear(input, self.mask * self.weight, self.bias)
+        return F.linear(input, self.masked_weight(), self.bias)
 
 
 class MADE(nn.Module):
@@ -291,6 +325,23 @@ class MADE(nn.Module):
             return (x - mu) * torch.exp(-sigma)
         return self.net(x)
 
+    # ----- sampling support: only the outputs one dimension needs ------------------------------------------------
+    def hidden_forward(self, x):
+        """Activation of the last hidden layer (everything but the final MaskedLinear)."""
+        a = x
+        for layer in list(self.net)[:-1]:
+            a = layer(a)
+        return a
+
+    def output_columns(self, hidden, first, stride):
+        """Outputs `first, first + stride, first + 2*stride, ...` of the final MaskedLinear for `hidden` =
+        hidden_forward(x): out[:, first::stride] of the full forward without evaluating the other columns.
+        UMNNMAF.invert (UMNNMAF.py:199-202) needs the E values h[:, e*D + j] for ONE dimension j per step, while the
+        final layer has E*D outputs (23 520 at the MNIST shape)."""
+        last = list(self.net)[-1]
+        wm = last.masked_weight()
+        return F.linear(hidden, wm[first::stride], last.bias[first::stride])
+
     def compute_ll(self, x):
         mu, sigma = self._gaussian_params(x)
         z = (x - mu) * torch.exp(-sigma)
@@ -321,6 +372,16 @@ class ConditionnalMADE(MADE):
 
     def forward(self, x, context):
         return self._strip_context(super().forward(torch.cat((context, x), 1)), x.shape[0])
+
+    def hidden_forward(self, x, context=None):
+        return super().hidden_forward(x if context is None else torch.cat((context, x), 1))
+
+    def output_columns(self, hidden, first, stride):
+        """Columns first::stride of forward()'s (context-stripped) output: chunk e of the raw output keeps its
+        entries cond_in.., so stripped column e*nin_non_cond + j is raw column e*nin + cond_in + j."""
+        if stride != self.nin_non_cond:
+            raise ValueError("ConditionnalMADE.output_columns: stride must be the number of data dimensions")
+        return super().output_columns(hidden, self.cond_in + first, self.nin)
 
     def invert(self, z, context=None):
         """Signature and the `None` return for non-Gaussian heads follow made.py:181-192.  The reference's loop body
