@@ -30,7 +30,9 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
-GOLDEN_CASES = ["cfg1_monotonic", "cfg1_monotonic_x0", "cfg2_toy", "cfg3_power", "cfg3_power_trained",
+# cfg3_power_adam: integrand weights of a reference flow TRAINED for 300 Adam steps and the trained conditioner's h
+# (tests/golden/make_trained_golden.py); cfg3_power_trained: random weights scaled x2.5 ("trained-like")
+GOLDEN_CASES = ["cfg1_monotonic", "cfg1_monotonic_x0", "cfg2_toy", "cfg3_power", "cfg3_power_trained", "cfg3_power_adam",
                 "cfg4_bsds", "cfg5_mnist", "small_odd", "jit_shape"]
 
 
@@ -45,9 +47,12 @@ def load_golden_case(name):
     pseed, dseed = (int(v) for v in g["meta_seeds"])
     spec = orc.MLPSpec(tuple([1 + E] + hidden + [1]),
                        orc.HIDDEN_LEAKY if layout == "strided" else orc.HIDDEN_RELU, orc.OUT_ELU_PLUS_1)
-    flat = orc.synth_params(spec, pseed, float(g["meta_gain"]))
-    Hh = E * Dx if layout == "strided" else E
-    x0, x, h, go = orc.synth_inputs(B, Dx, Hh, dseed, bool(g["meta_x0_zero"]))
+    if "stored_flat" in g:      # trained weights / real conditioner outputs travel in the file
+        flat, x0, x, h, go = (g[k] for k in ("stored_flat", "stored_x0", "stored_x", "stored_h", "stored_grad_out"))
+    else:
+        flat = orc.synth_params(spec, pseed, float(g["meta_gain"]))
+        Hh = E * Dx if layout == "strided" else E
+        x0, x, h, go = orc.synth_inputs(B, Dx, Hh, dseed, bool(g["meta_x0_zero"]))
     m = hashlib.sha256()
     for a in (flat, x0, x, h, go):
         m.update(np.ascontiguousarray(a).tobytes())

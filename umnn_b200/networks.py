@@ -260,7 +260,10 @@ class MaskedLinear(nn.Linear):
         (no_grad / eval inference, sampling) the product is cached and reused until the weight or the mask changes
         (storage address + autograd version, as for the packed integrand parameters); with autograd on it is computed
         in the graph as in the reference."""
-        if torch.is_grad_enabled() and self.weight.requires_grad:
+        if (torch.is_grad_enabled() and self.weight.requires_grad) or \
+                (self.weight.is_cuda and torch.cuda.is_current_stream_capturing()):
+            # (while a CUDA graph is being captured the product must be a node of the graph: replays read the live
+            # weights, umnn_b200/graphs.py)
             return self.mask * self.weight
         stamp = (self.weight.data_ptr(), self.weight._version, self.mask.data_ptr(), self.mask._version, self.weight.device)
         hit = self.__dict__.get("_masked_cache")
