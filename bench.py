@@ -173,6 +173,15 @@ def reference_step(ref, net, x, h, Q):
     return z, jac
 
 
+def host_threads():
+    """All the host cores this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+    silently turn the CPU arms into single-thread runs: the arms set the thread count explicitly instead."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def reference_cpu_arm(cfg, flat, budget_s, n_threads=0):
     """The unmodified reference on the host cores, bounded sample of the workload, batch-chunked like the reference's
     own drivers sub-batch (MNISTExperiment.py:46,160).  Returns (evals/s, info) or None if the reference is absent."""
@@ -180,8 +189,7 @@ def reference_cpu_arm(cfg, flat, budget_s, n_threads=0):
     ref = load_reference()
     if ref is None:
         return None
-    if n_threads:
-        torch.set_num_threads(n_threads)
+    torch.set_num_threads(n_threads or host_threads())
     threads = torch.get_num_threads()
     D, E, Q = cfg["D"], cfg["E"], cfg["Q"]
     Hh = E * D if cfg["layout"] == "strided" else E
@@ -244,6 +252,7 @@ def run_reference(args, cfg, name):
     Hh = E * D if cfg["layout"] == "strided" else E
     ref = load_reference()
     if ref is not None:
+        torch.set_num_threads(host_threads())
         threads = torch.get_num_threads()
         net = reference_integrand(ref, cfg, flat, "cpu")
         # size one step at ~2 s of CPU work so K + W steps end within a couple of minutes
