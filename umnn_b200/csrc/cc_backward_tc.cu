@@ -102,7 +102,8 @@ __global__ void __launch_bounds__(kThreads, 1) cc_dgrad_tc_kernel(const __grid_c
 #else
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 #endif
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform role index (see cc_forward_tc.cu)
     const uint32_t rank = cluster_ctarank();
     const TcDgradLayout& L = p.L;
     const int T = p.tiles_per_cta, J = L.J;
@@ -160,9 +161,12 @@ __global__ void __launch_bounds__(kThreads, 1) cc_dgrad_tc_kernel(const __grid_c
         mbar_wait(&bars[BAR_WLOAD], 0, 100);
         if (elect_one_sync()) mbar_arrive_cluster(&bars[BAR_PEER], 0);
         __syncwarp();
-        if (rank == 0) {
-            mbar_wait(&bars[BAR_PEER], 0, 101);
-            const uint32_t sbase = smem_u32(smem);
+        // lane-0 broadcasts keep the issuer's descriptors / tensor-memory addresses in uniform registers (cc_forward_tc.cu)
+        const uint32_t rank_u = __shfl_sync(0xffffffffu, rank, 0);
+        const uint32_t tbase = __shfl_sync(0xffffffffu, *holder, 0);
+        if (rank_u == 0) {
+            mbar_wait_warp(&bars[BAR_PEER], 0, 101);
+            const uint32_t sbase = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
             for (int t = 0; t < T; ++t) {
                 const uint32_t par = (uint32_t)(t & 1);
                 for (int m = 0; m < J; ++m) {
@@ -181,15 +185,12 @@ __global__ void __launch_bounds__(kThreads, 1) cc_dgrad_tc_kernel(const __grid_c
                         uint32_t a_hi = a_base;
                         for (int kb = 0; kb < n_kb; ++kb) {
                             if (s == 0 && (kb & 1) == 0) {
-                                mbar_wait(&ready[kb >> 1], par, 200 + m * 8 + (kb >> 1));
+                                mbar_wait_warp(&ready[kb >> 1], par, 200 + m * 8 + (kb >> 1));
                                 tc_fence_after_sync();
                             }
-                            if (elect_one_sync()) {
-                                mma_ts<2>(d_addr, a_hi, bhi, idesc, kb > 0);
-                                mma_ts<2>(d_addr, a_hi + 8, bhi, idesc, 1);
-                                mma_ts<2>(d_addr, a_hi, blo, idesc, 1);
-                            }
-                            __syncwarp();
+                            mma_ts_elect<2>(d_addr, a_hi, bhi, idesc, kb > 0);
+                            mma_ts_elect<2>(d_addr, a_hi + 8, bhi, idesc, 1);
+                            mma_ts_elect<2>(d_addr, a_hi, blo, idesc, 1);
                             a_hi += 16;
                             bhi += step;
                             blo += step;
@@ -502,7 +503,8 @@ __global__ void __launch_bounds__(kWThreads, 1) cc_wgrad_tc_kernel(const __grid_
     __shared__ __align__(8) uint64_t full[kWMaxStages], empty[kWMaxStages], done, peer_ready[kWMaxStages];
     const int kWStages = p.n_stages;
     __shared__ uint32_t holder;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform role index (see cc_forward_tc.cu)
     const uint32_t rank = cluster_ctarank();
     const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
     const TcWgradPlan& W = p.W;
@@ -535,7 +537,10 @@ __global__ void __launch_bounds__(kWThreads, 1) cc_wgrad_tc_kernel(const __grid_
     const uint32_t tbase = holder;
 
     const int kbs = W.kb_per_stage;
-    const long long n_st = (n_kb + kbs - 1) / kbs;            // pipeline stages this pair walks
+    // pipeline stages this pair walks; 32-bit counters and a rolling (stage, phase) pair below: a 64-bit division
+    // in these loops would be a subroutine call, which costs the MMA issuer its uniform registers
+    const int n_kb32 = (int)n_kb;
+    const int n_st = (n_kb32 + kbs - 1) / kbs;
 
     if (warp == kWEpiWarps) {
         // =========================================================== producer: ONE bulk-TMA copy per panel and stage
@@ -557,77 +562,68 @@ __global__ void __launch_bounds__(kWThreads, 1) cc_wgrad_tc_kernel(const __grid_
         }
         __syncwarp();
         const uint32_t n_copies = n_copies_s, blk_bytes = blk_bytes_s;
-        for (long long si = 0; si < n_st; ++si) {
-            const int st = (int)(si % kWStages);
-            if (si >= kWStages) mbar_wait(&empty[st], (uint32_t)((si / kWStages - 1) & 1), 400 + st);
-            const long long kb0 = si * kbs;
-            const uint32_t nb = (uint32_t)((n_kb - kb0 < kbs) ? (n_kb - kb0) : kbs);     // blocks in this stage (tail: fewer)
+        int st = 0;
+        uint32_t round = 0;                                   // how many times the ring has wrapped
+        for (int si = 0; si < n_st; ++si) {
+            if (round > 0) mbar_wait(&empty[st], (round - 1) & 1u, 400 + st);
+            const int kb0 = si * kbs;
+            const uint32_t nb = (uint32_t)((n_kb32 - kb0 < kbs) ? (n_kb32 - kb0) : kbs);     // blocks in this stage (tail: fewer)
             if (lane == 0) mbar_expect_tx(&full[st], nb * blk_bytes);
             __syncwarp();
             uint8_t* sb = smem + (size_t)st * W.stage_bytes;
             const unsigned long long blk = (unsigned long long)(blk_begin + kb0);
             for (uint32_t i = lane; i < n_copies; i += 32)
                 bulk_g2s(sb + cp_dst[i], reinterpret_cast<const uint8_t*>(cp_src[i] + blk * cp_blk_bytes[i]), nb * cp_blk_bytes[i], &full[st]);
+            if (++st == kWStages) { st = 0; ++round; }
         }
         __syncwarp();
     } else if (warp == kWEpiWarps + 1) {
         // =========================================================== MMA issuer
-        // Per layer the four operand descriptors of (stage 0, block 0) are built once; a later stage / block only adds
-        // its byte offset (>> 4) to the descriptor's address field (shared-memory addresses stay below 2^18, so the
-        // 14-bit field never carries).
-        __shared__ unsigned long long d_ahi[UMNN_MAX_LAYERS], d_alo[UMNN_MAX_LAYERS], d_bhi[UMNN_MAX_LAYERS], d_blo[UMNN_MAX_LAYERS];
-        __shared__ uint32_t d_idesc[UMNN_MAX_LAYERS], d_mstep[UMNN_MAX_LAYERS], d_nstep[UMNN_MAX_LAYERS], d_flags[UMNN_MAX_LAYERS];
-        const uint32_t sbase = smem_u32(smem);
-        if (lane == 0) {
-            for (int l = 0; l < W.n_layers; ++l) {
-                const TcWgradLayer& y = W.layer[l];
-                // tiles hold [block][hi | lo] x [k8][W/16 core matrices]; the M tile is read 128 rows deep although only
-                // W/2 are staged (rows beyond feed accumulator rows nobody reads)
-                const uint32_t lbo_m = (uint32_t)(y.m_width / 16) * 128u, lbo_n = (uint32_t)(y.n_width / 16) * 128u;
-                d_ahi[l] = make_smem_desc(sbase + W.tile_off[y.m_panel], lbo_m, 128);
-                d_alo[l] = make_smem_desc(sbase + W.tile_off[y.m_panel] + 16u * y.m_width, lbo_m, 128);
-                d_bhi[l] = make_smem_desc(sbase + W.tile_off[y.n_panel], lbo_n, 128);
-                d_blo[l] = make_smem_desc(sbase + W.tile_off[y.n_panel] + 16u * y.n_width, lbo_n, 128);
-                d_idesc[l] = make_idesc_bf16_f32(256, y.n_width) | (1u << 15) | (1u << 16);
-                d_mstep[l] = W.block_bytes[y.m_panel] >> 4;
-                d_nstep[l] = W.block_bytes[y.n_panel] >> 4;
-                // hi*hi always; the cross terms only for operands whose panel carries a lo part
-                d_flags[l] = (W.panel_parts[y.m_panel] == 2 ? 1u : 0u) | (W.panel_parts[y.n_panel] == 2 ? 2u : 0u);
-            }
-        }
-        __syncwarp();
+        // Converged warp, warp-uniform control flow (votes in the waits, election inside the MMA statement): the operand
+        // descriptors are rebuilt per layer and stage from kernel parameters with uniform-datapath arithmetic.
+        const uint32_t rank_u = __shfl_sync(0xffffffffu, rank, 0);
+        const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0);
+        const uint32_t sbase = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
         const int n_layers = W.n_layers;
-        for (long long si = 0; si < n_st; ++si) {
-            const int st = (int)(si % kWStages);
-            const uint32_t ph = (uint32_t)((si / kWStages) & 1);
-            mbar_wait(&full[st], ph, 410 + st);
+        int st = 0;
+        uint32_t ph = 0;
+        for (int si = 0; si < n_st; ++si) {
+            mbar_wait_warp(&full[st], ph, 410 + st);
             // both CTAs' tiles of this stage must have landed before the pair-wide MMA reads them
             if (elect_one_sync()) mbar_arrive_cluster(&peer_ready[st], 0);
             __syncwarp();
-            if (rank == 0) {
-                mbar_wait(&peer_ready[st], ph, 420 + st);
+            if (rank_u == 0) {
+                mbar_wait_warp(&peer_ready[st], ph, 420 + st);
                 tc_fence_after_sync();
-                const long long kb0 = si * kbs;
-                const int nb = (int)((n_kb - kb0 < kbs) ? (n_kb - kb0) : kbs);
-                const unsigned long long st_off = (unsigned long long)(((uint32_t)st * W.stage_bytes) >> 4);
-                if (elect_one_sync()) {
-                    for (int l = 0; l < n_layers; ++l) {
-                        const uint32_t idesc = d_idesc[l], fl = d_flags[l];
-                        const uint32_t d_addr = tbase + (uint32_t)W.layer[l].tmem_col;
-                        unsigned long long ahi = d_ahi[l] + st_off, alo = d_alo[l] + st_off, bhi = d_bhi[l] + st_off, blo = d_blo[l] + st_off;
-                        const unsigned long long ms = d_mstep[l], ns = d_nstep[l];
-                        for (int i = 0; i < nb; ++i) {
-                            mma_ss<2>(d_addr, ahi, bhi, idesc, (si > 0 || i > 0) ? 1u : 0u);
-                            if (fl & 1u) mma_ss<2>(d_addr, alo, bhi, idesc, 1);
-                            if (fl & 2u) mma_ss<2>(d_addr, ahi, blo, idesc, 1);
-                            ahi += ms; alo += ms; bhi += ns; blo += ns;
-                        }
+                const int kb0 = si * kbs;
+                const int nb = (n_kb32 - kb0 < kbs) ? (n_kb32 - kb0) : kbs;
+                const uint32_t stage_addr = sbase + (uint32_t)st * W.stage_bytes;
+                for (int l = 0; l < n_layers; ++l) {
+                    const TcWgradLayer& y = W.layer[l];
+                    const uint32_t idesc = make_idesc_bf16_f32(256, y.n_width) | (1u << 15) | (1u << 16);
+                    // tiles hold [block][hi | lo] x [k8][W/16 core matrices]; the M tile is read 128 rows deep although only
+                    // W/2 are staged (rows beyond feed accumulator rows nobody reads)
+                    const uint32_t lbo_m = (uint32_t)(y.m_width / 16) * 128u, lbo_n = (uint32_t)(y.n_width / 16) * 128u;
+                    uint64_t ahi = make_smem_desc(stage_addr + W.tile_off[y.m_panel], lbo_m, 128);
+                    uint64_t bhi = make_smem_desc(stage_addr + W.tile_off[y.n_panel], lbo_n, 128);
+                    const uint64_t a_lo_off = (uint64_t)((16u * (uint32_t)y.m_width) >> 4), b_lo_off = (uint64_t)((16u * (uint32_t)y.n_width) >> 4);
+                    const uint64_t ms = (uint64_t)(W.block_bytes[y.m_panel] >> 4), ns = (uint64_t)(W.block_bytes[y.n_panel] >> 4);
+                    // hi*hi always; the cross terms only for operands whose panel carries a lo part
+                    const bool m_lo = W.panel_parts[y.m_panel] == 2, n_lo = W.panel_parts[y.n_panel] == 2;
+                    const uint32_t d_addr = tb + (uint32_t)y.tmem_col;
+                    for (int i = 0; i < nb; ++i) {
+                        mma_ss_elect<2>(d_addr, ahi, bhi, idesc, (si > 0 || i > 0) ? 1u : 0u);
+                        if (m_lo) mma_ss_elect<2>(d_addr, ahi + a_lo_off, bhi, idesc, 1);
+                        if (n_lo) mma_ss_elect<2>(d_addr, ahi, bhi + b_lo_off, idesc, 1);
+                        ahi += ms;
+                        bhi += ns;
                     }
-                    // release the stage in BOTH CTAs once these MMAs have read it
-                    mma_commit<2>(&empty[st], 0x3);
                 }
+                // release the stage in BOTH CTAs once these MMAs have read it
+                if (elect_one_sync()) mma_commit<2>(&empty[st], 0x3);
                 __syncwarp();
             }
+            if (++st == kWStages) { st = 0; ph ^= 1u; }
         }
         if (rank == 0) {
             if (elect_one_sync()) mma_commit<2>(&done, 0x3);

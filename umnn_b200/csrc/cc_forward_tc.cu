@@ -157,7 +157,10 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 #endif
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // broadcast from lane 0: the compiler then knows the warp index -- and every role branch on it -- is warp-uniform
+    // (uniform registers for descriptors and addresses inside the MMA-issuer branch)
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const uint32_t rank = cluster_ctarank();
     const TcLayout& L = p.L;
     const int T = p.tiles_per_cta;
@@ -207,17 +210,6 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
     cluster_sync_all();
     tc_fence_after_sync();
     const uint32_t tbase = *holder;
-    if (NARROW && tid == 0) {
-        // two CTA pairs share an SM pair here: the pair-collective allocation must have handed both CTAs of THIS
-        // pair the same columns (one tcgen05.mma addresses the tensor memory of both)
-        uint32_t peer_base;
-        asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(peer_base) : "r"(map_to_cta(smem_u32(holder), rank ^ 1u)) : "memory");
-        if (peer_base != tbase) {
-            printf("cc_forward_tc: tensor-memory base differs inside CTA pair (block %d: %u vs %u)\n", (int)blockIdx.x, tbase, peer_base);
-            __trap();
-        }
-    }
-
     if (warp == kMmaWarp) {
         // =========================================================== MMA issuer warp
         // The whole warp runs this code converged (uniform control flow keeps descriptors and TMEM
@@ -235,9 +227,21 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
         mbar_wait(&bars[BAR_WLOAD], 0, 100);
         if (elect_one_sync()) mbar_arrive_cluster(&bars[BAR_PEER], 0);   // this CTA's half of B is resident
         __syncwarp();
-        if (rank == 0) {
-            mbar_wait(&bars[BAR_PEER], 0, 101);
-            const uint32_t sbase = smem_u32(smem);
+        // lane-0 broadcasts: values the compiler cannot see as warp-uniform on its own (special-register reads through
+        // asm, a shared-memory load) become uniform-register material
+        const uint32_t rank_u = __shfl_sync(0xffffffffu, rank, 0);
+        const uint32_t tbase = __shfl_sync(0xffffffffu, *holder, 0);
+        if (NARROW) {
+            // two CTA pairs share an SM pair here: the pair-collective allocation must have handed both CTAs of THIS
+            // pair the same columns (one tcgen05.mma addresses the tensor memory of both).  Checked by the whole warp
+            // with a warp-uniform outcome (a divergent branch here would cost the issuer its uniform registers).
+            uint32_t peer_base;
+            asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(peer_base) : "r"(map_to_cta(smem_u32(holder), rank ^ 1u)) : "memory");
+            if (__any_sync(0xffffffffu, peer_base != tbase)) asm volatile("trap;");
+        }
+        if (rank_u == 0) {
+            mbar_wait_warp(&bars[BAR_PEER], 0, 101);
+            const uint32_t sbase = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
             for (int t = 0; t < T; ++t) {
                 const uint32_t par = (uint32_t)(t & 1);
                 for (int m = 0; m < L.n_mma; ++m) {
@@ -256,15 +260,12 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
                         uint32_t a_hi = a_base;
                         for (int kb = 0; kb < n_kb; ++kb) {
                             if (s == 0 && (kb & 1) == 0) {
-                                mbar_wait(&ready[kb >> 1], par, 200 + m * 8 + (kb >> 1));
+                                mbar_wait_warp(&ready[kb >> 1], par, 200 + m * 8 + (kb >> 1));
                                 tc_fence_after_sync();
                             }
-                            if (elect_one_sync()) {
-                                mma_ts<2>(d_addr, a_hi, bhi, idesc, kb > 0);
-                                mma_ts<2>(d_addr, a_hi + 8, bhi, idesc, 1);
-                                mma_ts<2>(d_addr, a_hi, blo, idesc, 1);
-                            }
-                            __syncwarp();
+                            mma_ts_elect<2>(d_addr, a_hi, bhi, idesc, kb > 0);
+                            mma_ts_elect<2>(d_addr, a_hi + 8, bhi, idesc, 1);
+                            mma_ts_elect<2>(d_addr, a_hi, blo, idesc, 1);
                             a_hi += 16;
                             bhi += step;
                             blo += step;

@@ -102,9 +102,12 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 #ifndef UMNN_TC_SPIN_LIMIT
 #define UMNN_TC_SPIN_LIMIT (1LL << 32)
 #endif
-static __device__ __noinline__ void mbar_wait_expired(int tag, uint32_t parity) {
-    printf("mbar_wait timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x, (int)threadIdx.x, parity);
-    __trap();
+// No printf here: a device-side call anywhere in the kernel makes ptxas give up uniform registers for values that are
+// live across it (they are caller-saved through vector registers), and the MMA issuer's descriptors are live across
+// every wait.  The trap surfaces as cudaErrorLaunchFailure; `tag` / parity stay in registers for cuda-gdb.
+__device__ __forceinline__ void mbar_wait_expired(int tag, uint32_t parity) {
+    (void)tag; (void)parity;
+    asm volatile("trap;");
 }
 // UMNN_TC_WAIT_STYLE: 1 (default) = read the clock after every failed poll; 0 = clock every 4096 polls; 2 = poll
 // count only (2^27 polls), no clock.  A/B on one B200 (scripts/gpu_visit_r1k.sh, ms per step, config 4 at
@@ -151,6 +154,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
             else if (now - t0 > (unsigned long long)(UMNN_TC_SPIN_LIMIT)) mbar_wait_expired(tag, parity);
         }
     }
+#endif
+}
+// The same wait for a warp that must stay CONVERGED (the MMA issuer): every lane probes and the loop exit is a warp
+// vote, i.e. a warp-uniform condition.  With a per-lane exit condition ptxas treats everything after the loop as
+// possibly divergent and keeps descriptors / tensor-memory addresses in vector registers, paying an R2UR per operand
+// of every tcgen05.mma (18 per K block, ~50 instructions between two MMA triples -- more than the MMAs take on narrow
+// layers); with the vote they live in uniform registers.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int tag = 0) {
+    if (__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) return;
+#if UMNN_TC_SPIN_LIMIT
+    const unsigned long long t0 = global_timer_ns();
+    while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity)))
+        if (global_timer_ns() - t0 > (unsigned long long)(UMNN_TC_SPIN_LIMIT)) mbar_wait_expired(tag, parity);
+#else
+    (void)tag;
+    while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {}
 #endif
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int tag = 0) {
@@ -296,6 +315,36 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
         asm volatile(
             "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
             "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+}
+// The same TS MMA issued from CONVERGED code: every lane executes the statement, the election happens inside it and
+// only the elected lane's tcgen05.mma is issued.  Unlike `if (elect_one_sync()) mma_ts(...)`, the operands are used by
+// convergent code, so warp-uniform descriptors / addresses can stay in uniform registers instead of being broadcast
+// from the elected lane's vector registers before every MMA.
+template <int CG>
+__device__ __forceinline__ void mma_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (CG == 1)
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void mma_ss_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (CG == 1)
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
             : "memory");
 }
 // mbarrier arrive (count 1) once every previously issued tcgen05.mma of this thread has completed.
