@@ -13,7 +13,7 @@
  *     the host.  The *_host entry points take HOST pointers and are synchronous.
  *   - return value: 0 = ok; negative = argument error (UMNN_ERR_*); positive = cudaError_t.
  *     `umnn_last_error()` returns a thread-local human-readable message for the last failure.
- *   - re-entrant; no global mutable state except the thread-local error string.
+ *   - re-entrant; no global mutable state except the thread-local error string and an atomic call counter.
  *   - all tensors are contiguous float32.  B = n_samples, Dx = n_dims, E = n_ctx, Q = nb_steps
  *     (Q+1 quadrature nodes).
  *
@@ -148,7 +148,10 @@ UMNN_API size_t umnn_workspace_bytes(const umnn_desc* desc, int32_t for_backward
  *   out_f_at_x    [B][Dx] or NULL;  out_f_at_x0 [B][Dx] or NULL
  *   nodes, weights  device tables of Q+1 floats (umnn_cc_tables / compute_cc_weights)
  *   workspace     umnn_workspace_bytes(desc, 0) bytes, or NULL (UMNN_PREC_FP16X3 then runs unguarded: an activation
- *                 beyond the fp16 range surfaces as NaN)
+ *                 beyond the fp16 range surfaces as NaN).  Its content on entry does not matter and the same buffer may
+ *                 serve every call that is ordered on one stream: the overflow flag is marked with a per-call value
+ *                 (a process-wide atomic counter, the library's only mutable global besides the error string)
+ *                 instead of being cleared, so a guarded call is two launches and no memset.
  */
 UMNN_API int umnn_cc_forward(const umnn_desc* desc, const float* x0, const float* x, const float* h,
                     const void* params_packed, const float* nodes, const float* weights,

@@ -903,7 +903,7 @@ int launch_backward_tc(const umnn_desc* d, const float* x0, const float* x, cons
             // pass F
             int rc = launch_forward_tc_emit(d, x0, x, h, fp16_act ? (const uint8_t*)fwd_blobs_fp16 : fwd_blobs, nodes, weights, s0, cs,
                                             B.slots_per_cta, B.tiles, B.n_cta, emit, fp16_act ? UMNN_OPF_FP16 : UMNN_OPF_BF16,
-                                            run_if, fp16_act ? flag : nullptr, s);
+                                            run_if, fp16_act ? flag : nullptr, 1, s);
             if (rc) return rc;
             // pass D
             g.slot0 = s0;

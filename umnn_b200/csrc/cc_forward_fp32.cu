@@ -35,7 +35,8 @@ struct FwdParams {
     float* out;
     float* out_fx;
     float* out_fx0;
-    const int* run_if;     // not NULL: no-op unless *run_if != 0 (guarded re-run of an FP16X3 call)
+    const int* run_if;     // not NULL: no-op unless *run_if == run_epoch (guarded re-run of an FP16X3 call)
+    int run_epoch;
     long long n_slots;
     long long slots_per_cta;
     int D, E, layout, Q, rps, n_layers, hidden_act, out_act;
@@ -64,7 +65,7 @@ __device__ __forceinline__ const float* slot_ctx(const FwdParams& p, long long s
 
 template <int HIDDEN_ACT>
 __global__ void __launch_bounds__(512) cc_forward_fp32_kernel(const FwdParams p) {
-    if (p.run_if != nullptr && *p.run_if == 0) return;
+    if (p.run_if != nullptr && *p.run_if != p.run_epoch) return;
     extern __shared__ __align__(16) float smem[];
     float* act = smem;                                        // [max_kpad][kTile]
     float* wst = act + (size_t)p.max_kpad * kTile;            // [2][kKC][max_npad]
@@ -289,10 +290,11 @@ int launch_pack_fp32(const umnn_desc* d, const float* flat, float* packed, cudaS
 
 int launch_forward_fp32(const umnn_desc* d, const float* x0, const float* x, const float* h, const float* packed,
                         const float* nodes, const float* weights, float* out, float* out_fx, float* out_fx0,
-                        const int* run_if, cudaStream_t s) {
+                        const int* run_if, int run_epoch, cudaStream_t s) {
     const Fp32Layout L = make_fp32_layout(d);
     FwdParams p{};
     p.run_if = run_if;
+    p.run_epoch = run_epoch;
     p.x0 = x0; p.x = x; p.h = h; p.packed = packed; p.nodes = nodes; p.weights = weights;
     p.out = out; p.out_fx = out_fx; p.out_fx0 = out_fx0;
     p.n_slots = d->n_samples * (long long)d->n_dims;

@@ -147,7 +147,7 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
     // that NaN to 0, so ReLU networks track the largest converted value instead.
     constexpr bool kTrack = (OPF == UMNN_OPF_FP16) && (HIDDEN_ACT == UMNN_ACT_RELU);
     // guarded re-run (see launch_forward_tc): nothing to do unless the first attempt raised the flag
-    if (p.run_if != nullptr && *p.run_if == 0) return;
+    if (p.run_if != nullptr && *p.run_if != p.epoch) return;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte aligned base, by pointer arithmetic on the __shared__ array so that the compiler keeps the
     // address space (LDS/STS instead of generic LD/ST on every table and scratch access)
@@ -292,14 +292,23 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
                 const long long last = (row0 + kTcTile < n_rows ? row0 + kTcTile : n_rows) - 1;
                 ns = (int)(last / p.rps - ls_first) + 1;
             }
-            // context of the slots this tile touches -> shared memory (one gather per value)
-            if (live)
-                for (int idx = ptid; idx < ns * p.E; idx += kPrepThreads) {
-                    const int i = idx / p.E, e = idx - i * p.E;
-                    int hs;
-                    const float* hp = slot_ctx(p, slot_begin + ls_first + i, &hs);
-                    hbuf[idx] = __ldg(hp + (long long)e * hs);
+            // context of the slots this tile touches -> shared memory.  STRIDED_D stores h as [B][E][D]: the slots of a
+            // tile are consecutive in d, so the slot index runs fastest over the threads -- neighbouring lanes read
+            // neighbouring floats of one 32-byte sector (the e-major order fetched a sector per lane).  CONTIG ([N][E])
+            // is contiguous in e.
+            if (live) {
+                if (p.layout == UMNN_LAYOUT_STRIDED_D) {
+                    for (int idx = ptid; idx < ns * p.E; idx += kPrepThreads) {
+                        const int e = idx / ns, i = idx - e * ns;
+                        int hs;
+                        const float* hp = slot_ctx(p, slot_begin + ls_first + i, &hs);
+                        hbuf[i * p.E + e] = __ldg(hp + (long long)e * hs);
+                    }
+                } else {
+                    const float* hp = p.h + (slot_begin + ls_first) * (long long)p.E;      // ns * E contiguous floats
+                    for (int idx = ptid; idx < ns * p.E; idx += kPrepThreads) hbuf[idx] = __ldg(hp + idx);
                 }
+            }
             for (int r = ptid; r < kTcTile; r += kPrepThreads) {
                 const long long row = row0 + r;
                 float xi = 0.0f;
@@ -572,7 +581,7 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
                 if (EMIT) p.emit.v[cta_row0 + row0 + r] = node >= 0 ? vtot : 0.0f;
                 if (node >= 0) {
                     // fp16 operands, LeakyReLU: an overflowed activation has made this row's output NaN (see kTrack)
-                    if (OPF == UMNN_OPF_FP16 && !kTrack && p.raise_flag != nullptr && !(fabsf(vtot) <= 3.0e38f)) *p.raise_flag = 1;
+                    if (OPF == UMNN_OPF_FP16 && !kTrack && p.raise_flag != nullptr && !(fabsf(vtot) <= 3.0e38f)) *p.raise_flag = p.epoch;
                     const float f = out_act(vtot, p.out_act);
                     if (node <= p.Q) {
                         fval[r] = f * tab_w[node];
@@ -615,7 +624,7 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
             if (lane == 0) mbar_arrive(&bars[BAR_PREP_EMPTY + b]);
         }
         // ReLU networks: an activation beyond the fp16 range became inf in its operand -> ask for the bf16 re-run
-        if (kTrack && p.raise_flag != nullptr && amax > kFp16Max) *p.raise_flag = 1;
+        if (kTrack && p.raise_flag != nullptr && amax > kFp16Max) *p.raise_flag = p.epoch;
     }
 
     // ---------------------------------------------------------------- teardown
@@ -779,7 +788,7 @@ size_t tc_packed_bytes(const umnn_desc* d) {
 
 int launch_forward_tc(const umnn_desc* d, const float* x0, const float* x, const float* h, const void* packed,
                       const float* nodes, const float* weights, float* out, float* out_fx, float* out_fx0,
-                      int opf, const int* run_if, int* raise_flag, cudaStream_t s) {
+                      int opf, const int* run_if, int* raise_flag, int epoch, cudaStream_t s) {
     TcParams p{};
     if (!make_tc_layout(d, &p.L, tc_two_segments())) {
         set_error("tensor-core forward: shape not supported");
@@ -787,7 +796,7 @@ int launch_forward_tc(const umnn_desc* d, const float* x0, const float* x, const
     }
     p.x0 = x0; p.x = x; p.h = h; p.nodes = nodes; p.weights = weights; p.blobs = (const uint8_t*)packed;
     p.out = out; p.out_fx = out_fx; p.out_fx0 = out_fx0;
-    p.run_if = run_if; p.raise_flag = raise_flag;
+    p.run_if = run_if; p.raise_flag = raise_flag; p.epoch = epoch;
     p.n_slots = d->n_samples * (long long)d->n_dims;
     p.D = d->n_dims; p.E = d->n_ctx; p.layout = d->layout; p.Q = d->nb_steps; p.out_act = d->out_act;
     p.rps = d->nb_steps + 1 + (out_fx ? 1 : 0) + (out_fx0 ? 1 : 0);
@@ -864,7 +873,7 @@ int tc_forward_occupancy(const umnn_desc* d, int extra_rows, int* narrow_out, in
 int launch_forward_tc_emit(const umnn_desc* d, const float* x0, const float* x, const float* h, const void* packed,
                            const float* nodes, const float* weights, long long slot0, long long n_slots_chunk,
                            long long slots_per_cta, int tiles_per_cta, int n_cta, const TcEmit& emit, int opf,
-                           const int* run_if, int* raise_flag, cudaStream_t s) {
+                           const int* run_if, int* raise_flag, int epoch, cudaStream_t s) {
     TcParams p{};
     if (!make_tc_layout(d, &p.L, tc_two_segments())) {
         set_error("BF16X3: shape not supported by the tensor-core kernel");
@@ -872,7 +881,7 @@ int launch_forward_tc_emit(const umnn_desc* d, const float* x0, const float* x, 
     }
     p.x0 = x0; p.x = x; p.h = h; p.nodes = nodes; p.weights = weights; p.blobs = (const uint8_t*)packed;
     p.out = nullptr; p.out_fx = nullptr; p.out_fx0 = nullptr;
-    p.run_if = run_if; p.raise_flag = raise_flag;
+    p.run_if = run_if; p.raise_flag = raise_flag; p.epoch = epoch;
     p.slot0 = slot0; p.n_slots = n_slots_chunk; p.slots_per_cta = slots_per_cta; p.tiles_per_cta = tiles_per_cta;
     p.D = d->n_dims; p.E = d->n_ctx; p.layout = d->layout; p.Q = d->nb_steps; p.out_act = d->out_act;
     p.rps = d->nb_steps + 3;

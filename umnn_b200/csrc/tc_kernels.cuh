@@ -33,8 +33,9 @@ struct TcParams {
     int tiles_per_cta;
     int D, E, layout, Q, rps, out_act;
     int x_row;             // 1: the first extra row of a slot (node Q+1) is evaluated at x, else at x0
-    const int* run_if;     // not NULL: the whole launch is a no-op unless *run_if != 0 (guarded bf16 re-run)
-    int* raise_flag;       // not NULL (fp16 operands): set when an activation overflowed the fp16 range
+    const int* run_if;     // not NULL: the whole launch is a no-op unless *run_if == epoch (guarded re-run)
+    int* raise_flag;       // not NULL (fp16 operands): set to `epoch` when an activation overflowed the fp16 range
+    int epoch;             // value that marks THIS call in the flag word (see umnn_cc_forward): no reset needed
     TcLayout L;
     TcSmem S;
     TcEmit emit;
@@ -43,7 +44,7 @@ struct TcParams {
 int launch_forward_tc_emit(const umnn_desc* d, const float* x0, const float* x, const float* h, const void* packed,
                            const float* nodes, const float* weights, long long slot0, long long n_slots_chunk,
                            long long slots_per_cta, int tiles_per_cta, int n_cta, const TcEmit& emit, int opf,
-                           const int* run_if, int* raise_flag, cudaStream_t s);
+                           const int* run_if, int* raise_flag, int epoch, cudaStream_t s);
 bool tc_two_segments_public();
 
 // tensor-core backward (cc_backward_tc.cu)

@@ -154,11 +154,11 @@ inline TcSmem make_tc_smem(const TcLayout& L, int rps, int Q) {
 
 // operand format of the MMA operands (weights blob and in-TMEM activations): UMNN_OPF_BF16 / UMNN_OPF_FP16
 int launch_pack_tc(const umnn_desc* d, const float* flat, void* packed, int opf, cudaStream_t s);
-// run_if (device int, may be NULL): the launch is a no-op unless *run_if != 0.  raise_flag (device int, may be
-// NULL; fp16 operands only): set to 1 when an activation overflowed the fp16 range.
+// run_if (device int, may be NULL): the launch is a no-op unless *run_if == epoch.  raise_flag (device int, may be
+// NULL; fp16 operands only): set to `epoch` when an activation overflowed the fp16 range.
 int launch_forward_tc(const umnn_desc* d, const float* x0, const float* x, const float* h, const void* packed,
                       const float* nodes, const float* weights, float* out, float* out_fx, float* out_fx0,
-                      int opf, const int* run_if, int* raise_flag, cudaStream_t s);
+                      int opf, const int* run_if, int* raise_flag, int epoch, cudaStream_t s);
 int tc_forward_occupancy(const umnn_desc* d, int extra_rows, int* narrow_out, int* ctas_per_sm);
 size_t tc_packed_bytes(const umnn_desc* d);
 // 0 if the tensor-core kernel can serve desc (with `extra_rows` = 0..2 extra rows per slot), else a reason string

@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <vector>
 
 #include "umnn_common.cuh"
@@ -113,6 +114,19 @@ static size_t tc_fp32_offset(const umnn_desc* d) { return (tc_fp16_offset(d) + t
 static bool bwd_rerun_is_fp32(const umnn_desc* d) { return backward_fp32_unsupported_reason(d) == nullptr; }
 
 constexpr size_t kFlagBytes = 256;   // head of the workspace of a guarded FP16X3 call: one int flag
+
+// Marks of the guarded forward calls (see umnn_cc_forward).  Process-wide counter, values >= 2 (0 = cleared by a
+// memset, 1 = the mark of memset-based sequences: the backward and calls issued under CUDA-graph capture).
+static std::atomic<uint32_t> g_forward_epoch{2};
+static int next_epoch() {
+    uint32_t e = g_forward_epoch.fetch_add(1, std::memory_order_relaxed);
+    while (e < 2 || e > 0x7fffffffu) {            // wrapped: restart above the reserved values
+        uint32_t expected = e + 1;
+        g_forward_epoch.compare_exchange_strong(expected, 3);
+        e = g_forward_epoch.fetch_add(1, std::memory_order_relaxed);
+    }
+    return (int)e;
+}
 
 }  // namespace umnn
 
@@ -267,11 +281,11 @@ int umnn_cc_forward(const umnn_desc* d, const float* x0, const float* x, const f
     switch (resolve_precision(d)) {
         case UMNN_PREC_FP32:
             return launch_forward_fp32(d, x0, x, h, (const float*)params_packed, nodes, weights, out_integral,
-                                       out_f_at_x, out_f_at_x0, nullptr, (cudaStream_t)stream);
+                                       out_f_at_x, out_f_at_x0, nullptr, 0, (cudaStream_t)stream);
         case UMNN_PREC_BF16X3:
             if ((rc = check_tc(d, "umnn_cc_forward")) != 0) return rc;
             return launch_forward_tc(d, x0, x, h, params_packed, nodes, weights, out_integral, out_f_at_x,
-                                     out_f_at_x0, UMNN_OPF_BF16, nullptr, nullptr, (cudaStream_t)stream);
+                                     out_f_at_x0, UMNN_OPF_BF16, nullptr, nullptr, 0, (cudaStream_t)stream);
         case UMNN_PREC_FP16X3: {
             // fp16 hi/lo operands carry 22 bits (bf16: ~17) but overflow above 65504.  Guarded: the kernel raises a
             // device flag when an activation overflowed (every downstream value is NaN then), and a second launch --
@@ -281,15 +295,24 @@ int umnn_cc_forward(const umnn_desc* d, const float* x0, const float* x, const f
             if ((rc = check_tc(d, "umnn_cc_forward")) != 0) return rc;
             const uint8_t* fp16_blobs = (const uint8_t*)params_packed + tc_fp16_offset(d);
             int* flag = nullptr;
+            int epoch = 1;
             if (workspace && workspace_bytes >= sizeof(int)) {
                 flag = (int*)workspace;
-                UMNN_CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), (cudaStream_t)stream));
+                // The flag word is never reset between calls: the fp16 kernel raises it by writing THIS call's mark
+                // and the re-run launch runs only if it reads that mark back, so whatever an earlier call (or the
+                // allocator) left in the word is ignored -- one stream operation less per call.  A chance match with
+                // uninitialised memory (2^-31) costs a redundant FP32 re-run, never a wrong result.  Under CUDA-graph
+                // capture the mark would be frozen into the graph, so captured sequences clear the word first.
+                cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+                UMNN_CUDA_TRY(cudaStreamIsCapturing((cudaStream_t)stream, &cap));
+                if (cap != cudaStreamCaptureStatusNone) UMNN_CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), (cudaStream_t)stream));
+                else epoch = next_epoch();
             }
             rc = launch_forward_tc(d, x0, x, h, fp16_blobs, nodes, weights, out_integral, out_f_at_x, out_f_at_x0,
-                                   UMNN_OPF_FP16, nullptr, flag, (cudaStream_t)stream);
+                                   UMNN_OPF_FP16, nullptr, flag, epoch, (cudaStream_t)stream);
             if (rc || !flag) return rc;
             return launch_forward_fp32(d, x0, x, h, (const float*)((const uint8_t*)params_packed + tc_fp32_offset(d)), nodes,
-                                       weights, out_integral, out_f_at_x, out_f_at_x0, flag, (cudaStream_t)stream);
+                                       weights, out_integral, out_f_at_x, out_f_at_x0, flag, epoch, (cudaStream_t)stream);
         }
         default:
             set_error("umnn_cc_forward: precision %d is not available for this shape", d->precision);

@@ -126,11 +126,11 @@ __device__ __forceinline__ float upper_limit(float x0, float x, int Q) {
 // launchers implemented in the kernel translation units
 namespace umnn {
 int launch_pack_fp32(const umnn_desc* d, const float* flat, float* packed, cudaStream_t s);
-// run_if != NULL: every kernel of the launch is a no-op unless *run_if != 0 (the guarded FP32 re-run of an FP16X3
-// call whose activations left the fp16 range, see umnn_cc_forward / umnn_cc_backward)
+// run_if != NULL: every kernel of the launch is a no-op unless *run_if == run_epoch (the guarded FP32 re-run of an
+// FP16X3 call whose activations left the fp16 range, see umnn_cc_forward / umnn_cc_backward)
 int launch_forward_fp32(const umnn_desc* d, const float* x0, const float* x, const float* h, const float* packed,
                         const float* nodes, const float* weights, float* out, float* out_fx, float* out_fx0,
-                        const int* run_if, cudaStream_t s);
+                        const int* run_if, int run_epoch, cudaStream_t s);
 // fused FP32 backward (cc_backward_fp32.cu).  budget_bytes > 0: size the chunks to fill a workspace of that many
 // bytes (fewer launches; used by the guarded re-run, which borrows the tensor-core backward's workspace) instead of
 // the L2-sized default.
