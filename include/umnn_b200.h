@@ -224,6 +224,27 @@ UMNN_API int umnn_invert_bracket_step(int64_t n_samples, int32_t n_grid, const f
                              int64_t bracket_stride, float* x_grid_next, float* x_mid, int64_t x_mid_stride,
                              void* stream);
 
+/*
+ * Sampling direction, one whole dimension per call: everything UMNNMAF.invert does for dimension j after the
+ * conditioner pass (models/UMNN/UMNNMAF.py:203-231) -- replicate the dimension's context over the grid, reset the
+ * bracket to [init_left, init_right] (the reference starts every dimension at [-50, 50], :194-195), then n_iter rounds
+ * of {umnn_cc_forward over the n_grid * n_samples grid slots, umnn_invert_bracket_step} -- enqueued by ONE call
+ * (1 + 3 * n_iter launches) instead of ~25 host-side operations per round.
+ *   desc        UMNN_LAYOUT_CONTIG descriptor of the grid integrals: n_samples MUST be n_grid * n_samples, n_dims 1
+ *   h_cols      [n_samples][E]   context of dimension j (h[:, j::D]); column 0 is the offset z0
+ *   grid        [n_grid] relative grid positions; scale: device pointer to exp(scaling[j])
+ *   target      z[:, j] with element stride target_stride
+ *   x_out       receives the closest grid point of the last round per sample, element stride x_out_stride
+ *               (write straight into x[:, j])
+ *   workspace   umnn_invert_workspace_bytes(desc, n_samples, n_grid) bytes
+ */
+UMNN_API size_t umnn_invert_workspace_bytes(const umnn_desc* desc, int64_t n_samples, int32_t n_grid);
+UMNN_API int umnn_invert_dimension(const umnn_desc* desc, const void* params_packed, const float* nodes,
+                          const float* weights, int64_t n_samples, int32_t n_grid, int32_t n_iter,
+                          const float* h_cols, const float* grid, const float* scale, const float* target,
+                          int64_t target_stride, float init_left, float init_right, float* x_out,
+                          int64_t x_out_stride, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -623,10 +623,10 @@ def test_invert_native_matches_op_by_op_loop(monkeypatch):
 
 
 @pytest.mark.parametrize("iters", [1, 6, 7])
-def test_invert_graph_replay_matches_launch_by_launch(monkeypatch, iters):
-    """One dimension's refinement rounds captured once and replayed per dimension (UMNN_B200_INVERT_GRAPH=1) against
-    the same launches issued one by one (default): identical results, also after a parameter update and for odd
-    round counts (grid ping-pong)."""
+def test_invert_dimension_call_matches_round_by_round(monkeypatch, iters):
+    """umnn_invert_dimension (one native call per dimension: context replication, bracket reset and all refinement
+    rounds enqueued from C, result written straight into x[:, j]) against the same launches issued round by round from
+    Python: identical results, also after a parameter update and for odd round counts (grid ping-pong)."""
     from umnn_b200 import UMNNMAFFlow
     torch.manual_seed(0)
     model = UMNNMAFFlow(nb_flow=1, nb_in=24, hidden_derivative=[50, 50, 50], hidden_embedding=[64, 64], embedding_s=10,
@@ -635,15 +635,39 @@ def test_invert_graph_replay_matches_launch_by_launch(monkeypatch, iters):
     z = torch.randn(16, 24, device=_dev())
     for attempt in range(2):
         with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
-            monkeypatch.setenv("UMNN_B200_INVERT_GRAPH", "1")
-            x_graph = model.invert(z, iter=iters)
-            monkeypatch.delenv("UMNN_B200_INVERT_GRAPH")
-            x_eager = model.invert(z, iter=iters)
-        assert torch.equal(x_graph, x_eager)
+            x_call = model.invert(z, iter=iters)
+            monkeypatch.setenv("UMNN_B200_INVERT", "rounds")
+            x_rounds = model.invert(z, iter=iters)
+            monkeypatch.delenv("UMNN_B200_INVERT")
+        assert torch.equal(x_call, x_rounds)
         with torch.no_grad():
             for p in model.parameters():
                 if p.requires_grad:
                     p.mul_(0.97)
+
+
+def test_invert_conditional_flow_and_partial_conditioner_outputs():
+    """EmbeddingNetwork.embedding_of_dim (the E rows of the last masked layer one dimension needs) against the full
+    conditioner pass, for plain and conditional MADE, on the device; and invert() of a conditional flow."""
+    from umnn_b200 import EmbeddingNetwork, UMNNMAFFlow
+    torch.manual_seed(1)
+    for cond in (0, 3):
+        emb = EmbeddingNetwork(7, [64, 64], [32, 32], 6, cond_in=cond, device=_dev())
+        x = torch.randn(9, 7, device=_dev())
+        ctx = torch.randn(9, cond, device=_dev()) if cond else None
+        with torch.no_grad():
+            full = emb.make_embeding(x, ctx)
+            for j in range(7):
+                assert torch.allclose(emb.embedding_of_dim(x, j, ctx), full[:, j::7], rtol=1e-5, atol=1e-6)
+    model = UMNNMAFFlow(nb_flow=1, nb_in=5, hidden_derivative=[50, 50], hidden_embedding=[64, 64], embedding_s=8, nb_steps=20,
+                        solver="CCParallel", cond_in=2, device=_dev()).to(_dev())
+    model.eval()
+    x = 0.5 * torch.randn(12, 5, device=_dev())
+    ctx = torch.randn(12, 2, device=_dev())
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        z = model.forward(x, context=ctx)
+        x_back = model.invert(z, iter=8, context=ctx)
+    assert float((x_back - x).abs().max()) < 5e-2
 
 
 def test_monotonic_nn_on_cuda():

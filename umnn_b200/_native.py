@@ -25,7 +25,8 @@ PREC_FP32, PREC_BF16X3, PREC_AUTO, PREC_FP16X3 = 0, 1, 2, 3
 
 EXPORTS = ("umnn_abi_version", "umnn_last_error", "umnn_cc_tables", "umnn_param_count",
            "umnn_packed_params_bytes", "umnn_packed_layout_id", "umnn_pack_params", "umnn_workspace_bytes", "umnn_cc_forward",
-           "umnn_cc_backward", "umnn_cc_forward_host", "umnn_invert_bracket_step", "umnn_tc_forward_occupancy")
+           "umnn_cc_backward", "umnn_cc_forward_host", "umnn_invert_bracket_step", "umnn_tc_forward_occupancy",
+           "umnn_invert_workspace_bytes", "umnn_invert_dimension")
 
 
 class Desc(ctypes.Structure):
@@ -90,6 +91,11 @@ def lib() -> ctypes.CDLL:
         L.umnn_invert_bracket_step.restype = ctypes.c_int
         L.umnn_invert_bracket_step.argtypes = [i64, ctypes.c_int32, fp, fp, fp, fp, i64, fp, fp, i64, fp, fp, i64, fp, fp,
                                                i64, vp]
+        L.umnn_invert_workspace_bytes.restype = ctypes.c_size_t
+        L.umnn_invert_workspace_bytes.argtypes = [dp, i64, ctypes.c_int32]
+        L.umnn_invert_dimension.restype = ctypes.c_int
+        L.umnn_invert_dimension.argtypes = [dp, vp, fp, fp, i64, ctypes.c_int32, ctypes.c_int32, fp, fp, fp, fp, i64,
+                                            ctypes.c_float, ctypes.c_float, fp, i64, vp, ctypes.c_size_t, vp]
         if L.umnn_abi_version() != UMNN_ABI_VERSION:
             raise RuntimeError(f"libumnn_b200.so ABI {L.umnn_abi_version()} != binding {UMNN_ABI_VERSION}; rebuild")
         _lib = L

@@ -18,11 +18,11 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import kernel
+from . import _native, kernel
 from .integral import (FusedIntegralAndPoint, NeuralIntegral, ParallelNeuralIntegral, fused_point_available,
                        integral_nograd, kernel_route)
 from .networks import (ConditionnalMADE, ContiguousIntegrand, IntegrandNN, IntegrandNetwork, MADE, _flatten, _mlp)
-from .quadrature import compute_cc_weights
+from .quadrature import compute_cc_weights, device_tables
 
 
 class EmbeddingNetwork(nn.Module):
@@ -238,15 +238,15 @@ class UMNNMAF(nn.Module):
 
 
     def _invert_native(self, z, iter, context, derivative, grid):
-        """invert() on the kernel route: per refinement round ONE fused integral launch over the 10*B grid slots
-        (contiguous-context layout) and ONE bracket-update launch (umnn_invert_bracket_step) instead of the
-        ~15 torch ops of UMNNMAF.py:213-231.  Same arithmetic, same results.
+        """invert() on the kernel route.  Per dimension: the conditioner's hidden layers plus ONLY the E rows of its last
+        masked layer that dimension reads (EmbeddingNetwork.embedding_of_dim; the reference evaluates all E*D outputs,
+        UMNNMAF.py:199-202), then ONE native call (umnn_invert_dimension) that enqueues the whole refinement of that
+        dimension -- context replication, bracket reset, and `iter` rounds of {fused integral over the 10*B grid slots,
+        fused bracket update} -- and writes the result straight into x[:, j].  Same arithmetic as the reference's
+        ~15 torch ops per round (UMNNMAF.py:203-231), bit-identical bracket logic.
 
-        The `iter` rounds of one dimension touch only fixed-size buffers and can be captured once per call as a CUDA
-        graph that is replayed for every dimension (UMNN_B200_INVERT_GRAPH=1, D >= 16).  Off by default: measured on
-        B200 the loop is bound by the conditioner pass and the kernels themselves, not by launches (MNIST shape,
-        D = 784, B = 16: 576 ms with the graph, 565 ms without; BSDS300 shape, D = 63: 56 vs 43 ms -- capture and
-        instantiation cost more than the launches saved)."""
+        UMNN_B200_INVERT=rounds keeps the previous form (two Python-level launches per round), =torch the
+        reference-shaped op-by-op loop."""
         n_grid = grid.shape[0]
         B, D = z.shape
         dev = z.device
@@ -255,7 +255,39 @@ class UMNNMAF(nn.Module):
         x_inv = torch.zeros(B, D, device=dev)
         s = torch.exp(self.scaling.detach()).to(dev).float().contiguous()
         E = spec.n_ctx
-        # fixed buffers of one dimension's refinement
+        if os.environ.get("UMNN_B200_INVERT", "") == "rounds":
+            return self._invert_native_rounds(z, iter, context, spec, grid, x_inv, s)
+        L = _native.lib()
+        probe = torch.empty(n_grid * B, 1, device=dev)
+        desc = kernel.make_desc(spec, probe, self.nb_steps)
+        ws_bytes = int(L.umnn_invert_workspace_bytes(desc, B, n_grid))
+        if ws_bytes == 0:
+            _native.check(-2)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        w_tab, t_tab = device_tables(self.nb_steps, dev)
+        grid = grid.float().contiguous()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.no_grad(), torch.cuda.device(dev):
+            for j in range(self.input_size):
+                if j % 100 == 0:
+                    print(j)
+                # only the E conditioner outputs dimension j reads
+                h_cols = self.net.embedding_of_dim(x_inv, j, context).float().contiguous()
+                packed = kernel.packed_parameters(spec, desc, dev)        # cached in eval mode, re-packed otherwise
+                rc = L.umnn_invert_dimension(desc, packed.data_ptr(), t_tab.data_ptr(), w_tab.data_ptr(), B, n_grid, int(iter),
+                                             h_cols.data_ptr(), grid.data_ptr(), s.data_ptr() + 4 * j, z.data_ptr() + 4 * j, D,
+                                             -50.0, 50.0, x_inv.data_ptr() + 4 * j, D, ws.data_ptr(), ws_bytes, stream)
+                if rc != 0:
+                    _native.check(rc)
+        return x_inv
+
+    def _invert_native_rounds(self, z, iter, context, spec, grid, x_inv, s):
+        """Round-by-round form of _invert_native (one fused integral launch + one bracket launch per round, issued from
+        Python); kept for A/B checks of umnn_invert_dimension."""
+        n_grid = grid.shape[0]
+        B, D = z.shape
+        dev = z.device
+        E = spec.n_ctx
         h_j = torch.empty(n_grid * B, E, device=dev)
         offset = torch.empty(B, device=dev)
         target = torch.empty(B, device=dev)
@@ -266,50 +298,21 @@ class UMNNMAF(nn.Module):
         x_a = torch.empty(n_grid, B, device=dev)
         x_b = torch.empty(n_grid, B, device=dev)
         integ = torch.empty(n_grid * B, 1, device=dev)
-
-        def rounds():
-            xa, xb = x_a, x_b
-            kernel.invert_bracket_step(None, None, grid, None, None, None, left, right, xa, None)
-            for _ in range(iter):
-                kernel.cc_forward(spec, None, xa.view(-1, 1), h_j, self.nb_steps, out=integ)
-                kernel.invert_bracket_step(integ.view(n_grid, B), xa, grid, offset, scale, target, left, right, xb, x_mid)
-                xa, xb = xb, xa
-
-        def load(j, h_cols):
-            h_j.view(n_grid, B, E).copy_(h_cols.unsqueeze(0).expand(n_grid, -1, -1))
-            offset.copy_(h_cols[:, 0])
-            target.copy_(z[:, j])
-            scale.copy_(s[j:j + 1])
-            left.fill_(-50.)
-            right.fill_(50.)
-
-        use_graph = os.environ.get("UMNN_B200_INVERT_GRAPH", "0") == "1" and D >= 16 and \
-            not torch.cuda.is_current_stream_capturing()
-        graph = None
         with torch.no_grad():
             for j in range(self.input_size):
-                if j % 100 == 0:
-                    print(j)
-                # only the E conditioner outputs dimension j reads (the reference runs the full MADE, UMNNMAF.py:199)
-                load(j, self.net.embedding_of_dim(x_inv, j, context).float())
-                if use_graph and graph is None:
-                    # first dimension: run eagerly on a side stream (loads the tables, packs the parameters, sizes the
-                    # allocator pools), then capture; the eager results are the first dimension's.  The graph lives
-                    # for this call only, so the packed parameters it reads cannot go stale.
-                    side = torch.cuda.Stream(device=dev)
-                    side.wait_stream(torch.cuda.current_stream(dev))
-                    with torch.cuda.stream(side):
-                        rounds()
-                    torch.cuda.current_stream(dev).wait_stream(side)
-                    x_inv[:, j] = x_mid
-                    graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(graph):
-                        rounds()
-                    continue
-                if graph is not None:
-                    graph.replay()
-                else:
-                    rounds()
+                h_cols = self.net.embedding_of_dim(x_inv, j, context).float()
+                h_j.view(n_grid, B, E).copy_(h_cols.unsqueeze(0).expand(n_grid, -1, -1))
+                offset.copy_(h_cols[:, 0])
+                target.copy_(z[:, j])
+                scale.copy_(s[j:j + 1])
+                left.fill_(-50.)
+                right.fill_(50.)
+                xa, xb = x_a, x_b
+                kernel.invert_bracket_step(None, None, grid, None, None, None, left, right, xa, None)
+                for _ in range(iter):
+                    kernel.cc_forward(spec, None, xa.view(-1, 1), h_j, self.nb_steps, out=integ)
+                    kernel.invert_bracket_step(integ.view(n_grid, B), xa, grid, offset, scale, target, left, right, xb, x_mid)
+                    xa, xb = xb, xa
                 x_inv[:, j] = x_mid
         return x_inv
 

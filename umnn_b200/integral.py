@@ -422,6 +422,21 @@ def cc_integrate_host(integrand, x_host, h_host, nb_steps, want_fx=False, out=No
         chunks = 4 if (x_host.numel() + h_host.numel()) * 4 >= (32 << 20) else 1
     chunks = max(1, min(int(chunks), B))
     bounds = [B * c // chunks for c in range(chunks + 1)]
+    if chunks == 1:
+        # small batches: everything on the current stream (no side streams, events or staging bookkeeping -- at a few
+        # thousand rows the host-side calls are the cost, not the copies)
+        with torch.no_grad():
+            xd = x_host.to(device, non_blocking=True)
+            hd = h_host.to(device, non_blocking=True)
+            spec = kernel_route(integrand, xd, xd, hd, False)
+            if spec is None:
+                raise ValueError("cc_integrate_host needs float32 inputs and a recognised integrand within the "
+                                 "kernel's limits")
+            od, fd, _ = kernel.cc_forward(spec, None, xd, hd, nb_steps, want_fx=want_fx, precision=precision)
+            out.copy_(od, non_blocking=True)
+            if want_fx:
+                fx_out.copy_(fd, non_blocking=True)
+        return out, (fx_out if want_fx else None)
     main = torch.cuda.current_stream(device)
     s_in, s_out = _side_streams(device)
     with torch.no_grad():
