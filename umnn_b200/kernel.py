@@ -18,9 +18,28 @@ _PRECISION_ENV = {"fp32": _native.PREC_FP32, "bf16x3": _native.PREC_BF16X3, "fp1
                   "auto": _native.PREC_AUTO}
 
 
+_ENV_DATA = getattr(os.environ, "_data", None)      # the raw bytes -> bytes dict behind os.environ (CPython, POSIX)
+
+
+def _env(name: bytes) -> Optional[bytes]:
+    """Current value of an environment switch.  os.environ.get() costs ~3 us per lookup (key encoding, value
+    decoding), which at seven lookups per call was most of a small launch's host time; the underlying dict is read
+    directly instead -- still live, so switches changed at run time (tests, A/B scripts) are seen."""
+    if _ENV_DATA is not None:
+        return _ENV_DATA.get(name)
+    v = os.environ.get(name.decode())
+    return None if v is None else v.encode()
+
+
+_PRECISION_ENV_B = {k.encode(): v for k, v in _PRECISION_ENV.items()}
+
+
 def default_precision() -> int:
     """UMNN_B200_PRECISION = fp32 | bf16x3 | fp16x3 | auto (default auto)."""
-    return _PRECISION_ENV[os.environ.get("UMNN_B200_PRECISION", "auto").lower()]
+    v = _env(b"UMNN_B200_PRECISION")
+    if v is None:
+        return _native.PREC_AUTO
+    return _PRECISION_ENV_B[v.lower()]
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -138,7 +157,7 @@ def _desc_info(spec: KernelSpec, desc: _native.Desc, what: str):
     dkey = getattr(desc, "_umnn_key", None)
     if dkey is None:        # a descriptor built elsewhere: ask the library directly
         return int(L.umnn_packed_layout_id(desc)) if what == "layout" else int(L.umnn_workspace_bytes(desc, 0 if what == "ws0" else 1))
-    env = (os.environ.get("UMNN_B200_TC_SEGMENTS"), os.environ.get("UMNN_B200_BWD_PANELS"), os.environ.get("UMNN_B200_TC_NARROW"))
+    env = (_env(b"UMNN_B200_TC_SEGMENTS"), _env(b"UMNN_B200_BWD_PANELS"), _env(b"UMNN_B200_TC_NARROW"), _env(b"UMNN_B200_WGRAD_KBS"))
     key = (dkey, what, env)
     hit = spec.info_cache.get(key)
     if hit is not None:
@@ -253,7 +272,7 @@ def backward_precision(spec: KernelSpec, x: torch.Tensor, nb_steps: int) -> Opti
 
     UMNN_B200_BACKWARD = auto (default: tensor cores, else FFMA) | fp16x3 | bf16x3 | fp32 | torch.
     """
-    mode = os.environ.get("UMNN_B200_BACKWARD", "auto").lower()
+    mode = (_env(b"UMNN_B200_BACKWARD") or b"auto").decode().lower()
     if mode == "torch":
         return None
     if mode == "bf16x3":
