@@ -218,11 +218,14 @@ def kernel_route(integrand, x0, x, h, inv_f=False):
         raise UnsupportedIntegrandError(
             f"umnn_b200: {type(integrand).__name__} is outside the fused kernel's limits ({why}). "
             "Set UMNN_B200_ALLOW_TORCH_ROUTE=1 to evaluate it with PyTorch ops instead.")
-    if not (x0.is_cuda and h.is_cuda and x0.device == x.device and h.device == x.device):
+    dev = x.device
+    if not (x0.is_cuda and h.is_cuda and x0.device == dev and h.device == dev):
         raise ValueError("umnn_b200: x0, x and h must live on the same CUDA device")
-    for p in spec.parameters():
-        if p.device != x.device or p.dtype != torch.float32:
-            raise ValueError("umnn_b200: the integrand's parameters must be float32 on the same CUDA device as x")
+    # the first parameter is checked on every call, all of them whenever the parameters are (re)packed
+    # (kernel.packed_parameters): a per-parameter device comparison costs more than the rest of a small launch
+    p0 = spec.param_list[0]
+    if p0.device != dev or p0.dtype != torch.float32:
+        raise ValueError("umnn_b200: the integrand's parameters must be float32 on the same CUDA device as x")
     return spec
 
 

@@ -98,6 +98,9 @@ def packed_parameters(spec: KernelSpec, desc: _native.Desc, device: torch.device
     if nbytes == 0:
         msg = L.umnn_last_error()
         raise _native.NativeError(_native_err_unsupported, msg.decode("utf-8", "replace") if msg else "")
+    for p in spec.param_list:
+        if p.device != device or p.dtype != torch.float32:
+            raise ValueError("umnn_b200: the integrand's parameters must be float32 on the same CUDA device as x")
     packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
     flat = _as_f32c(flat_parameters(spec))
     stream = torch.cuda.current_stream(device).cuda_stream

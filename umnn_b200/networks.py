@@ -85,7 +85,15 @@ class KernelSpec:
         return iter(self.param_list)
 
     def supported(self) -> Optional[str]:
-        """None if the kernel can serve this shape, else the reason."""
+        """None if the kernel can serve this shape, else the reason (memoised: the shape is fixed per spec)."""
+        hit = self.info_cache.get("supported", False)
+        if hit is not False:
+            return hit
+        why = self._supported()
+        self.info_cache["supported"] = why
+        return why
+
+    def _supported(self) -> Optional[str]:
         if len(self.widths) - 1 > _native.UMNN_MAX_LAYERS:
             return f"{len(self.widths) - 1} Linear layers > {_native.UMNN_MAX_LAYERS}"
         if len(self.widths) < 3:
