@@ -208,15 +208,15 @@ __global__ void __launch_bounds__(kThreads, 1) cc_dgrad_tc_kernel(const __grid_c
         for (int u = 0; u < T; ++u) {
             const int b = u % kTcPrepBufs;
             if (u >= kTcPrepBufs) mbar_wait(&bars[BAR_PREP_EMPTY + b], (uint32_t)((u / kTcPrepBufs - 1) & 1), 120 + b);
-            const long long row0 = (long long)u * kTcTile;
+            const uint32_t row0 = (uint32_t)u * kTcTile;          // 32-bit row arithmetic: a chunk holds <= 4096 rows per CTA
             for (int r = ptid; r < kTcTile; r += kPrepThreads) {
-                const long long row = row0 + r;
+                const uint32_t row = row0 + r;
                 const long long pr = cta_row0 + row;
                 float dv = 0.0f, f = 0.0f;
                 int node = -1;
-                if (row < n_rows) {
-                    const long long ls = row / p.rps;
-                    node = (int)(row - ls * p.rps);
+                if (row < (uint32_t)n_rows) {
+                    const uint32_t ls = row / (uint32_t)p.rps;
+                    node = (int)(row - ls * (uint32_t)p.rps);
                     const long long slot = slot_begin + ls;
                     const float v = p.v[pr];
                     f = out_act(v, p.out_act);
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1) cc_dgrad_tc_kernel(const __grid_c
         auto head_pair = [&](int bu, int tile, int pp) {
             const long long pr = cta_row0 + (long long)tile * kTcTile + r;
             const float dv = dvrow[bu * kTcTile + r];
-            const uint32_t bits = p.mask[J][pr * 8 + pp];
+            const uint32_t bits = p.mask[J][(long long)pp * p.r_pad + pr];
             const int halves = (32 * pp + 16 < PJ) ? 2 : 1;
             const PanelRow prow = panel_row(p.dz[J], pr, PJ, p.dz_parts, p.r_pad);
 #pragma unroll
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(kThreads, 1) cc_dgrad_tc_kernel(const __grid_c
                 const int n_pairs = (y.npad + 31) / 32;
                 for (int pp = cg; pp < n_pairs; pp += kColGroups) {
                     const int s = (y.nseg == 2 && 32 * pp >= y.seg_begin[1]) ? 1 : 0;
-                    const uint32_t bits = p.mask[jout][pr * 8 + pp];
+                    const uint32_t bits = p.mask[jout][(long long)pp * p.r_pad + pr];
                     mbar_wait(&bars[BAR_ACC + m * 2 + s], par, 300 + m * 2 + s);
                     tc_fence_after_sync();
                     const uint32_t taddr = tbase + lane_sel + col_d + 32u * pp;
@@ -369,39 +369,54 @@ __global__ void __launch_bounds__(kThreads, 1) cc_dgrad_tc_kernel(const __grid_c
             }
 
             // ---- per-slot context gradient (carried across tiles), Leibniz terms, Jacobian-point term of d_x
-            const long long row0 = (long long)t * kTcTile;
-            if (row0 < n_rows) {
-                const long long last_row = (row0 + kTcTile < n_rows ? row0 + kTcTile : n_rows) - 1;
-                const long long s_first = row0 / p.rps, s_last = last_row / p.rps;
-                const int ns = (int)(s_last - s_first) + 1;
+            const int row0 = t * kTcTile, n_rows_i = (int)n_rows;
+            if (row0 < n_rows_i) {
+                const int last_row = (row0 + kTcTile < n_rows_i ? row0 + kTcTile : n_rows_i) - 1;
+                const int s_first = (int)((uint32_t)row0 / (uint32_t)p.rps), s_last = (int)((uint32_t)last_row / (uint32_t)p.rps);
+                const int ns = s_last - s_first + 1;
                 const float* cin = carry + (t & 1) * p.E;
                 float* cout = carry + ((t + 1) & 1) * p.E;
-                for (int idx = tid; idx < ns * p.E; idx += kEpiThreads) {
-                    const int i = idx / p.E, e = idx - i * p.E;
-                    const long long ls = s_first + i;
-                    const long long a = ls * p.rps, bb = a + p.rps - 1;
-                    const long long lo = a > row0 ? a : row0;
-                    const long long hi = bb < last_row ? bb : last_row;
-                    float sum = (a < row0) ? cin[e] : 0.0f;
-                    for (long long rr = lo; rr <= hi; ++rr) sum += d0[(int)(rr - row0) * d0_stride + 1 + e];
-                    if (bb <= last_row) {
-                        if (p.d_h) {
-                            const long long slot = slot_begin + ls;
-                            if (p.layout == UMNN_LAYOUT_STRIDED_D) {
-                                const long long n = slot / p.D;
-                                p.d_h[n * (long long)p.E * p.D + (long long)e * p.D + (slot - n * p.D)] = sum;
-                            } else {
-                                p.d_h[slot * (long long)p.E + e] = sum;
+                // every (slot, e) sum is split over kRedParts neighbouring lanes (rows lo + part, lo + part + kRedParts, ..)
+                // and combined by shuffles in a fixed order: the serial chain of one thread per (slot, e) -- up to rps
+                // dependent shared loads and adds, with every other epilogue warp parked at the barrier below -- was 12 %
+                // of this kernel's time
+                constexpr int kRedParts = 4;
+                const int n_items = ns * p.E * kRedParts;
+                for (int idx0 = 0; idx0 < n_items; idx0 += kEpiThreads) {      // warp-uniform trip count (shuffles inside)
+                    const int idx = idx0 + tid;
+                    const bool on = idx < n_items;
+                    const int part = idx & (kRedParts - 1), ie = idx / kRedParts;
+                    const int i = on ? ie / p.E : 0, e = on ? ie - i * p.E : 0;
+                    const int ls = s_first + i;
+                    const int a = ls * p.rps, bb = a + p.rps - 1;
+                    const int lo = a > row0 ? a : row0;
+                    const int hi = bb < last_row ? bb : last_row;
+                    float sum = 0.0f;
+                    if (on)
+                        for (int rr = lo + part; rr <= hi; rr += kRedParts) sum += d0[(rr - row0) * d0_stride + 1 + e];
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                    if (on && part == 0) {
+                        if (a < row0) sum += cin[e];
+                        if (bb <= last_row) {
+                            if (p.d_h) {
+                                const long long slot = slot_begin + ls;
+                                if (p.layout == UMNN_LAYOUT_STRIDED_D) {
+                                    const long long n = slot / p.D;
+                                    p.d_h[n * (long long)p.E * p.D + (long long)e * p.D + (slot - n * p.D)] = sum;
+                                } else {
+                                    p.d_h[slot * (long long)p.E + e] = sum;
+                                }
                             }
+                        } else {
+                            cout[e] = sum;
                         }
-                    } else {
-                        cout[e] = sum;
                     }
                 }
                 if (cg == 0) {
                     const int node = nodeid[b * kTcTile + r];
                     if (node > p.Q) {
-                        const long long slot = slot_begin + (row0 + r) / p.rps;
+                        const long long slot = slot_begin + (uint32_t)(row0 + r) / (uint32_t)p.rps;
                         const float g = p.grad_out[slot];
                         if (node == p.Q + 1) {
                             if (p.d_x) p.d_x[slot] = frow[b * kTcTile + r] * g + d0[r * d0_stride];

@@ -128,6 +128,7 @@ struct TcSmem {
     uint32_t off_cvec, off_hbuf, off_xnode, off_lsrel, off_node, off_part, off_fval, off_tabt, off_tabw, off_bars, off_holder;
     uint32_t total;
     int max_slots;
+    int h_stride;       // floats per slot row of hbuf: [h_0 .. h_{E-1}, 1.0, 0 ...], = round_up(E + 2, 16) = width of panel A_0
 };
 
 constexpr int kTcNumBars = kTcMaxMmaLayers * 10 /*ready[layer][8 pairs] + acc_full[layer][2]*/ + 2 * kTcPrepBufs + 2;
@@ -137,7 +138,10 @@ inline TcSmem make_tc_smem(const TcLayout& L, int rps, int Q) {
     S.max_slots = (kTcTile - 1) / rps + 2;   // slots a 128-row window can touch
     uint32_t off = L.blob_bytes;
     S.off_cvec = off;   off += 4u * kTcPrepBufs * S.max_slots * L.npad1;
-    S.off_hbuf = off;   off += 4u * S.max_slots * (L.E > 0 ? L.E : 1);
+    // a slot's context row is stored as the tail of its A_0 row ([x | h_0..h_{E-1}, 1, 0..]): 16-byte aligned for the
+    // float4 reads of the c_slot product, and pass F copies it into the A_0 panel without per-element branches
+    S.h_stride = round_up(L.E + 2, 16);
+    S.off_hbuf = off;   off += 4u * S.max_slots * S.h_stride;
     S.off_xnode = off;  off += 4u * kTcPrepBufs * kTcTile;
     S.off_lsrel = off;  off += 4u * kTcPrepBufs * kTcTile;
     S.off_node = off;   off += 4u * kTcPrepBufs * kTcTile;
