@@ -21,6 +21,7 @@ VARIANTS = {
     "lds_sleep50": ["-DUMNN_TC_WAIT_STYLE=3", "-DUMNN_TC_WAIT_SLEEP_NS=50"],
     "lds_sleep100": ["-DUMNN_TC_WAIT_STYLE=3", "-DUMNN_TC_WAIT_SLEEP_NS=100"],
     "lds_sleep200": ["-DUMNN_TC_WAIT_STYLE=3", "-DUMNN_TC_WAIT_SLEEP_NS=200"],
+    "issue_workconserving": ["-DUMNN_TC_ISSUE_WORKCONSERVING=1"],            # segment 1 advances while segment 0 waits (no gain measured: visit r2l)
     "lds_sleep50_nohint": ["-DUMNN_TC_WAIT_STYLE=3", "-DUMNN_TC_WAIT_SLEEP_NS=50", "-DUMNN_TC_WAIT_HINT=0"],
 }
 

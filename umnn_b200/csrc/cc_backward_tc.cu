@@ -174,30 +174,17 @@ __global__ void __launch_bounds__(kThreads, 1) cc_dgrad_tc_kernel(const __grid_c
                     const uint32_t a_base = tbase + ((m & 1) ? kColP : kColQ);
                     const uint32_t col_d = (m & 1) ? kColQ : kColP;
                     const int n_kb = y.kpad / 16;
-                    uint64_t* ready = &bars[BAR_READY + m * 8];
-                    for (int s = 0; s < y.nseg; ++s) {
-                        const uint32_t idesc = make_idesc_bf16_f32(256, y.seg_n[s]);
+                    MmaSegment gs[2];
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) {
                         const uint32_t lbo = (uint32_t)(y.seg_n[s] / 16) * 128u;
-                        const uint64_t step = (uint64_t)((2u * lbo) >> 4);
-                        const uint32_t d_addr = tbase + col_d + (uint32_t)y.seg_begin[s];
-                        uint64_t bhi = make_smem_desc(sbase + y.b_off[0][s], lbo, 128);
-                        uint64_t blo = make_smem_desc(sbase + y.b_off[1][s], lbo, 128);
-                        uint32_t a_hi = a_base;
-                        for (int kb = 0; kb < n_kb; ++kb) {
-                            if (s == 0 && (kb & 1) == 0) {
-                                mbar_wait_warp(&ready[kb >> 1], par, 200 + m * 8 + (kb >> 1));
-                                tc_fence_after_sync();
-                            }
-                            mma_ts_elect<2>(d_addr, a_hi, bhi, idesc, kb > 0);
-                            mma_ts_elect<2>(d_addr, a_hi + 8, bhi, idesc, 1);
-                            mma_ts_elect<2>(d_addr, a_hi, blo, idesc, 1);
-                            a_hi += 16;
-                            bhi += step;
-                            blo += step;
-                        }
-                        if (elect_one_sync()) mma_commit<2>(&bars[BAR_ACC + m * 2 + s], 0x3);
-                        __syncwarp();
+                        gs[s].idesc = make_idesc_bf16_f32(256, y.seg_n[s]);
+                        gs[s].step = (uint64_t)((2u * lbo) >> 4);
+                        gs[s].d_addr = tbase + col_d + (uint32_t)y.seg_begin[s];
+                        gs[s].bhi = make_smem_desc(sbase + y.b_off[0][s], lbo, 128);
+                        gs[s].blo = make_smem_desc(sbase + y.b_off[1][s], lbo, 128);
                     }
+                    issue_mma_layer(n_kb, y.nseg, gs[0], gs[1], a_base, &bars[BAR_READY + m * 8], par, &bars[BAR_ACC + m * 2], 200 + m * 8);
                 }
             }
         }

@@ -79,6 +79,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #endif
     return ok != 0;
 }
+// non-blocking probe (test_wait never suspends): the MMA issuer uses it to decide what to issue next
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // acquire at cluster scope: needed when the arrivals come from the peer CTA
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -356,6 +368,70 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar, uint16_t cta_mask = 0x
     else
         asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(cta_mask)
                      : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// One MMA layer of the activation chain (forward, pass F, pass D), issued by the converged issuer warp.
+//
+// The layer's N range is cut into one or two segments with separate accumulators; every K block is the hi/lo triple
+// D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo with A in tensor memory.  K block kb needs 32-column pair kb/2 of the A
+// operand, published by the epilogue warps on ready[kb/2].  Segment 0 is issued first (its commit starts the epilogue
+// that overlaps segment 1).  -DUMNN_TC_ISSUE_WORKCONSERVING=1 lets segment 1 advance on the pairs that are already
+// there whenever segment 0 is waiting for one that is not; measured on one box against the strict order it changes
+// nothing (forward 18.85 vs 18.91 ms at config 4 / 8192, pass F 258 vs 255 us, pass D 321 vs 318 us,
+// profiles/r2_issue_order_ab.txt): the chain MMA -> epilogue -> MMA of a tile is latency bound, the issuer's waits are
+// a symptom.  All decisions are warp votes or warp-uniform integers, so descriptors and addresses stay in uniform
+// registers (see mbar_wait_warp).
+// ---------------------------------------------------------------------------------------------
+struct MmaSegment {
+    uint32_t idesc;      // instruction descriptor (M = 256, N = segment width)
+    uint32_t d_addr;     // accumulator (tensor memory)
+    uint64_t bhi, blo;   // shared-memory descriptors of K block 0 (hi / lo part of B)
+    uint64_t step;       // descriptor increment per K block
+};
+
+__device__ __forceinline__ void mma_triple(const MmaSegment& g, uint32_t a_hi, uint64_t bhi, uint64_t blo, uint32_t accumulate) {
+    mma_ts_elect<2>(g.d_addr, a_hi, bhi, g.idesc, accumulate);
+    mma_ts_elect<2>(g.d_addr, a_hi + 8, bhi, g.idesc, 1);
+    mma_ts_elect<2>(g.d_addr, a_hi, blo, g.idesc, 1);
+}
+
+__device__ __forceinline__ void issue_mma_layer(int n_kb, int nseg, const MmaSegment& g0, const MmaSegment& g1, uint32_t a_base,
+                                                uint64_t* ready, uint32_t par, uint64_t* acc_bar, int tag) {
+    int kb0 = 0, kb1 = 0, known = 0;          // next K block per segment; pairs [0, known) are confirmed published
+    uint32_t a0 = a_base, a1 = a_base;
+    uint64_t bhi0 = g0.bhi, blo0 = g0.blo, bhi1 = g1.bhi, blo1 = g1.blo;
+    while (kb0 < n_kb) {
+        const int need = kb0 >> 1;
+        if (need >= known) {
+            if (__all_sync(0xffffffffu, mbar_test(&ready[need], par))) {
+                known = need + 1;
+                tc_fence_after_sync();
+#if defined(UMNN_TC_ISSUE_WORKCONSERVING) && UMNN_TC_ISSUE_WORKCONSERVING      // A/B switch, off in the product build (see above)
+            } else if (nseg == 2 && kb1 < n_kb && (kb1 >> 1) < known) {
+                mma_triple(g1, a1, bhi1, blo1, kb1 > 0);
+                a1 += 16; bhi1 += g1.step; blo1 += g1.step; ++kb1;
+                continue;
+#endif
+            } else {
+                mbar_wait_warp(&ready[need], par, tag + need);
+                known = need + 1;
+                tc_fence_after_sync();
+            }
+        }
+        mma_triple(g0, a0, bhi0, blo0, kb0 > 0);
+        a0 += 16; bhi0 += g0.step; blo0 += g0.step; ++kb0;
+    }
+    if (elect_one_sync()) mma_commit<2>(&acc_bar[0], 0x3);
+    __syncwarp();
+    if (nseg == 2) {
+        while (kb1 < n_kb) {
+            mma_triple(g1, a1, bhi1, blo1, kb1 > 0);         // every pair is confirmed: segment 0 has walked all of them
+            a1 += 16; bhi1 += g1.step; blo1 += g1.step; ++kb1;
+        }
+        if (elect_one_sync()) mma_commit<2>(&acc_bar[1], 0x3);
+        __syncwarp();
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
