@@ -196,6 +196,14 @@ __global__ void __launch_bounds__(kThreads, 1) cc_dgrad_tc_kernel(const __grid_c
             const int b = u % kTcPrepBufs;
             if (u >= kTcPrepBufs) mbar_wait(&bars[BAR_PREP_EMPTY + b], (uint32_t)((u / kTcPrepBufs - 1) & 1), 120 + b);
             const uint32_t row0 = (uint32_t)u * kTcTile;          // 32-bit row arithmetic: a chunk holds <= 4096 rows per CTA
+            // Pull this tile's sign masks (written by pass F, by now evicted to HBM) into L2 ahead of the epilogue warps:
+            // their mask loads sat on the critical path with DRAM latency (17 % of this kernel's stall samples).  A
+            // (layer, pair) run of 128 rows is 4 lines of 128 bytes.
+            for (int j = 1; j <= J; ++j) {
+                const int n_lines = ((L.P[j] + 31) / 32) * 4;
+                for (int idx = ptid; idx < n_lines; idx += kPrepThreads)
+                    prefetch_l2(p.mask[j] + (long long)(idx >> 2) * p.r_pad + cta_row0 + row0 + (idx & 3) * 32);
+            }
             for (int r = ptid; r < kTcTile; r += kPrepThreads) {
                 const uint32_t row = row0 + r;
                 const long long pr = cta_row0 + row;
@@ -246,6 +254,9 @@ __global__ void __launch_bounds__(kThreads, 1) cc_dgrad_tc_kernel(const __grid_c
         const TcChainLayer& ylast = L.layer[J - 1];
 
         mbar_wait(&bars[BAR_WLOAD], 0, 130);
+        // (sample, dimension) of the CTA's first slot: the one 64-bit division; slots further on use 32-bit arithmetic
+        const long long n_begin = p.layout == UMNN_LAYOUT_STRIDED_D ? slot_begin / p.D : 0;
+        const uint32_t d_begin = (uint32_t)(slot_begin - n_begin * p.D);
 
         // rank-1 head of the chain for tile `tile`: dz_J = dv * w_out (.) act'(a_J), 32 columns -> region Q
         auto head_pair = [&](int bu, int tile, int pp) {
@@ -389,8 +400,8 @@ __global__ void __launch_bounds__(kThreads, 1) cc_dgrad_tc_kernel(const __grid_c
                             if (p.d_h) {
                                 const long long slot = slot_begin + ls;
                                 if (p.layout == UMNN_LAYOUT_STRIDED_D) {
-                                    const long long n = slot / p.D;
-                                    p.d_h[n * (long long)p.E * p.D + (long long)e * p.D + (slot - n * p.D)] = sum;
+                                    const uint32_t dd = d_begin + (uint32_t)ls, dn = dd / (uint32_t)p.D;   // 32-bit: see n_begin
+                                    p.d_h[(n_begin + dn) * (long long)p.E * p.D + (long long)e * p.D + (dd - dn * (uint32_t)p.D)] = sum;
                                 } else {
                                     p.d_h[slot * (long long)p.E + e] = sum;
                                 }

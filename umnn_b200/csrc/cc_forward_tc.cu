@@ -77,17 +77,6 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 template <int N_THREADS>
 __device__ __forceinline__ void prep_bar_sync() { asm volatile("bar.sync 2, %0;" ::"n"(N_THREADS) : "memory"); }
 
-__device__ __forceinline__ const float* slot_ctx(const TcParams& p, long long slot, int* stride) {
-    if (p.layout == UMNN_LAYOUT_STRIDED_D) {
-        const long long n = slot / p.D;
-        const int d = (int)(slot - n * p.D);
-        *stride = p.D;
-        return p.h + n * (long long)p.E * p.D + d;
-    }
-    *stride = 1;
-    return p.h + slot * (long long)p.E;
-}
-
 template <int HIDDEN_ACT>
 __device__ __forceinline__ float hact(float v) {
     return HIDDEN_ACT == UMNN_ACT_LEAKY_RELU ? fmaxf(v, v * kLeakySlope) : fmaxf(v, 0.0f);
@@ -274,6 +263,8 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
         // divisions are subroutine calls on this ISA and the prep warps are the pacing resource of pass F.
         const int ptid = tid - kEpiThreads;
         const uint32_t n_rows32 = (uint32_t)n_rows, rps32 = (uint32_t)p.rps;
+        const long long n_begin = p.layout == UMNN_LAYOUT_STRIDED_D ? slot_begin / p.D : 0;   // the one 64-bit division
+        const uint32_t d_begin = (uint32_t)(slot_begin - n_begin * p.D);
         mbar_wait(&bars[BAR_WLOAD], 0, 110);
         for (int u = 0; u < T; ++u) {
             const int b = u % kTcPrepBufs;
@@ -294,9 +285,10 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
                 if (p.layout == UMNN_LAYOUT_STRIDED_D) {
                     for (int idx = ptid; idx < ns * p.E; idx += kPrepThreads) {
                         const int e = idx / ns, i = idx - e * ns;
-                        int hs;
-                        const float* hp = slot_ctx(p, slot_begin + ls_first + i, &hs);
-                        hbuf[i * Hs + e] = __ldg(hp + (long long)e * hs);
+                        // slot -> (sample, dimension) from the CTA's first slot with 32-bit arithmetic
+                        const uint32_t dd = d_begin + ls_first + (uint32_t)i, dn = dd / (uint32_t)p.D;
+                        const float* hp = p.h + (n_begin + dn) * (long long)p.E * p.D + (dd - dn * (uint32_t)p.D);
+                        hbuf[i * Hs + e] = __ldg(hp + (long long)e * p.D);
                     }
                 } else {
                     const float* hp = p.h + (slot_begin + ls_first) * (long long)p.E;      // ns * E contiguous floats
