@@ -7,7 +7,7 @@ from oracle import umnn_oracle as orc
 from umnn_b200 import IntegrandNetwork, kernel, _native
 SHAPES = {"cfg3": (10000, 6, 30, [200, 200, 200], 50), "cfg2": (10000, 2, 10, [100] * 4, 50),
           "cfg5": (100, 784, 30, [100, 50, 50, 50, 50], 50), "cfg4s": (1024, 63, 30, [200, 200, 200], 100),
-          "cfg4m": (8192, 63, 30, [200, 200, 200], 100)}
+          "cfg4m": (8192, 63, 30, [200, 200, 200], 100), "cfg3x4": (40000, 6, 30, [200, 200, 200], 50)}
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 B, D, E, hidden, Q = SHAPES[name]
@@ -33,4 +33,5 @@ ms = s.elapsed_time(e) / reps
 rows = B * D * (Q + 3)
 fpe = 2 * sum(a * b for a, b in zip(spec.widths[:-1], spec.widths[1:]))
 print(f"{name}: backward {ms:.3f} ms, {rows} rows, {ms * 1e6 / rows:.3f} ns/row, algorithmic {3 * fpe * rows / (ms * 1e-3) / 1e12:.1f} TFLOP/s "
-      f"[panels={os.environ.get('UMNN_B200_BWD_PANELS', 'auto')} kbs={os.environ.get('UMNN_B200_WGRAD_KBS', 'auto')}]", flush=True)
+      f"[panels={os.environ.get('UMNN_B200_BWD_PANELS', 'auto')} kbs={os.environ.get('UMNN_B200_WGRAD_KBS', 'auto')} "
+      f"overlap={os.environ.get('UMNN_B200_BWD_OVERLAP', 'auto')} wsms={os.environ.get('UMNN_B200_BWD_WSMS', '24')}]", flush=True)
