@@ -484,6 +484,43 @@ def test_native_backward_shapes(B, D, E, hidden, Q, layout, precision):
     assert_sum_grad_ok(got[2].cpu().numpy(), ref_flat.detach().cpu().numpy(), what="d_params vs torch ops")
 
 
+@pytest.mark.parametrize("layout,B,D,E,hidden,Q", [("contig", 100, 1, 2, [64, 64, 64], 50), ("strided", 37, 6, 30, [200, 200, 200], 50),
+                                                  ("strided", 5, 3, 4, [24, 16], 7)])
+def test_prepared_integral_matches_generic_entry(layout, B, D, E, hidden, Q):
+    """prepare_integral(...)(x, h) is the same launch as cc_integrate with the per-call host work resolved once: same
+    bits; parameters are snapshotted until refresh()."""
+    import umnn_b200
+    from umnn_b200 import cc_integrate
+    spec = orc.MLPSpec(tuple([1 + E] + hidden + [1]), orc.HIDDEN_LEAKY if layout == "strided" else orc.HIDDEN_RELU)
+    flat = orc.synth_params(spec, 2, 1.3)
+    net = _net_for(spec, flat, layout, D)
+    d = _dev()
+    g = torch.Generator(device=d).manual_seed(9)
+    x = 2 * torch.randn(B, D, device=d, generator=g)
+    x0 = 0.3 * torch.randn(B, D, device=d, generator=g)
+    h = torch.randn(B, (E * D) if layout == "strided" else E, device=d, generator=g)
+    prep = umnn_b200.prepare_integral(net, B, Q, want_fx=True, want_fx0=True)
+    for lo in (None, x0):
+        got = prep(x, h, lo)
+        ref = cc_integrate(net, lo, x, h, Q, want_fx=True, want_fx0=True)
+        for a, b in zip(got, ref):
+            assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        prep(x[:-1], h[:-1])
+    with pytest.raises(ValueError):
+        prep(x.double(), h)
+    # snapshot semantics
+    before = prep(x, h)[0].clone()
+    with torch.no_grad():
+        for p in net.parameters():
+            p.mul_(1.01)
+    assert torch.equal(prep(x, h)[0], before)
+    prep.refresh()
+    after = prep(x, h)[0]
+    # (same extra rows per slot as the prepared launch: the rows-to-tiles cut decides where a slot's node sum is split)
+    assert torch.equal(after, cc_integrate(net, None, x, h, Q, want_fx=True, want_fx0=True)[0]) and not torch.equal(after, before)
+
+
 # ---- full-size configurations (BASELINE.json): sampled oracle checks + size-independent properties ----
 def _full_size_check(B, D, E, hidden, Q, n_check, seed):
     from umnn_b200 import IntegrandNetwork, cc_integrate

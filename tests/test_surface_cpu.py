@@ -248,3 +248,13 @@ def test_made_is_autoregressive():
     for k in range(15):
         gx, = torch.autograd.grad(out[0, k], x, retain_graph=True)
         assert torch.all(gx[0, (k % 5):] == 0)         # output k%5 sees only inputs < k%5
+
+
+def test_prepare_integral_needs_cuda_and_a_recognised_integrand():
+    """prepare_integral is a kernel-route entry: no CPU fallback, no anonymous callables."""
+    import umnn_b200
+    net = umnn_b200.IntegrandNN(3, [16, 16])
+    with pytest.raises(ValueError):
+        umnn_b200.prepare_integral(net, 8, 10)                       # parameters live on the CPU
+    with pytest.raises(ValueError):
+        umnn_b200.prepare_integral(lambda x, h: x, 8, 10, device="cuda:0")

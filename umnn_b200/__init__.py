@@ -3,7 +3,7 @@ nn.Module / autograd.Function surface.  See DESIGN.md; the C ABI is in include/u
 from .flow import EmbeddingNetwork, MonotonicNN, UMNNMAF, UMNNMAFFlow  # noqa: F401
 from .graphs import GraphedLogLikelihood  # noqa: F401
 from .integral import (NeuralIntegral, ParallelNeuralIntegral, UnsupportedIntegrandError, cc_integrate,  # noqa: F401
-                       cc_integrate_host, integrate, integrate_sequential, torch_route)
+                       cc_integrate_host, integrate, integrate_sequential, prepare_integral, torch_route)
 from .kernel import invalidate_packed  # noqa: F401
 from .networks import (ConditionnalMADE, ContiguousIntegrand, ELUPlus, IntegrandNN, IntegrandNetwork,  # noqa: F401
                        MADE, MaskedLinear)

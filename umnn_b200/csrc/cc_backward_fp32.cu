@@ -551,9 +551,8 @@ int launch_backward_fp32(const umnn_desc* d, const float* x0, const float* x, co
     const Fp32Layout& L = B.L;
     const long long n_slots = d->n_samples * (long long)d->n_dims;
     int dev = 0, n_sm = 0;
-    UMNN_CUDA_TRY(cudaGetDevice(&dev));
-    UMNN_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    UMNN_CUDA_TRY(cudaFuncSetAttribute(cc_backward_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
+    UMNN_CUDA_TRY(current_device(&dev, &n_sm));
+    UMNN_CUDA_TRY(ensure_dynamic_smem((const void*)cc_backward_fp32_kernel, dev, (int)B.smem));
 
     float* scratch = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
     float* part = scratch + (size_t)B.floats_per_row * B.ld;

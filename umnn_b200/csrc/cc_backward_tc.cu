@@ -886,8 +886,10 @@ int launch_backward_tc(const umnn_desc* d, const float* x0, const float* x, cons
     for (int l = 0; l < d->n_layers; ++l) { w.src_w_off[l] = B.G.src_w_off[l]; w.src_b_off[l] = B.G.src_b_off[l]; }
 
     auto dkern = d->hidden_act == UMNN_ACT_LEAKY_RELU ? cc_dgrad_tc_kernel<UMNN_ACT_LEAKY_RELU> : cc_dgrad_tc_kernel<UMNN_ACT_RELU>;
-    UMNN_CUDA_TRY(cudaFuncSetAttribute(dkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.GS.total));
-    UMNN_CUDA_TRY(cudaFuncSetAttribute(cc_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.w_smem));
+    int dev = 0, n_sm_unused = 0;
+    UMNN_CUDA_TRY(current_device(&dev, &n_sm_unused));
+    UMNN_CUDA_TRY(ensure_dynamic_smem((const void*)dkern, dev, (int)B.GS.total));
+    UMNN_CUDA_TRY(ensure_dynamic_smem((const void*)cc_wgrad_tc_kernel, dev, (int)B.w_smem));
 
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;

@@ -309,8 +309,7 @@ int launch_forward_fp32(const umnn_desc* d, const float* x0, const float* x, con
     if (p.n_slots == 0) return 0;
 
     int dev = 0, n_sm = 0;
-    UMNN_CUDA_TRY(cudaGetDevice(&dev));
-    UMNN_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    UMNN_CUDA_TRY(current_device(&dev, &n_sm));
 
     const int n_groups = L.max_npad / kUT;
     const int threads = round_up(kRowGroups * n_groups, 32);  // 16 x ceil(maxH/8) rounded to whole warps, <= 512
@@ -318,9 +317,9 @@ int launch_forward_fp32(const umnn_desc* d, const float* x0, const float* x, con
 
     auto kern = d->hidden_act == UMNN_ACT_LEAKY_RELU ? cc_forward_fp32_kernel<UMNN_ACT_LEAKY_RELU>
                                                      : cc_forward_fp32_kernel<UMNN_ACT_RELU>;
-    UMNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    UMNN_CUDA_TRY(ensure_dynamic_smem((const void*)kern, dev, (int)smem));
     int occ = 0;
-    UMNN_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    UMNN_CUDA_TRY(cached_occupancy(&occ, (const void*)kern, dev, threads, smem));
     if (occ < 1) {
         set_error("cc_forward_fp32: kernel does not fit on an SM (threads=%d smem=%zu)", threads, smem);
         return UMNN_ERR_UNSUPPORTED;

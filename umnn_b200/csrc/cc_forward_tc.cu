@@ -736,9 +736,11 @@ template <int EMIT, bool NARROW, int OPF>
 int launch_tc_kernel(int hidden_act, const TcParams& p, int n_cta, cudaStream_t s) {
     auto kern = hidden_act == UMNN_ACT_LEAKY_RELU ? cc_forward_tc_kernel<UMNN_ACT_LEAKY_RELU, EMIT, NARROW, OPF>
                                                   : cc_forward_tc_kernel<UMNN_ACT_RELU, EMIT, NARROW, OPF>;
-    UMNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.S.total));
+    int dev = 0, n_sm_unused = 0;
+    UMNN_CUDA_TRY(current_device(&dev, &n_sm_unused));
+    UMNN_CUDA_TRY(ensure_dynamic_smem((const void*)kern, dev, (int)p.S.total));
     // two CTAs per SM need the full shared-memory carveout; without the hint the driver sizes it for one CTA
-    if (NARROW) UMNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (NARROW) UMNN_CUDA_TRY(ensure_max_carveout((const void*)kern, dev));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)n_cta);
     cfg.blockDim = dim3(Shape<NARROW>::kThreads);
@@ -812,8 +814,7 @@ int launch_forward_tc(const umnn_desc* d, const float* x0, const float* x, const
     // narrow shape: two co-resident CTAs per SM, each with half of the tensor memory
     const bool narrow = tc_narrow_enabled() && tc_layout_is_narrow(p.L) && p.S.total <= kTcNarrowMaxSmem;
     int dev = 0, n_sm = 0;
-    UMNN_CUDA_TRY(cudaGetDevice(&dev));
-    UMNN_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    UMNN_CUDA_TRY(current_device(&dev, &n_sm));
     const long long total_rows = p.n_slots * p.rps;
     long long n_cta = (total_rows + kTcTile - 1) / kTcTile;
     const long long cap = (long long)(n_sm / 2) * 2 * (narrow ? 2 : 1);
@@ -852,8 +853,10 @@ int tc_forward_occupancy(const umnn_desc* d, int extra_rows, int* narrow_out, in
     if (!ctas_per_sm) return 0;          // shape selection only: host arithmetic, no device needed
     const void* kern = narrow ? (const void*)cc_forward_tc_kernel<UMNN_ACT_LEAKY_RELU, 0, true, UMNN_OPF_FP16>
                               : (const void*)cc_forward_tc_kernel<UMNN_ACT_LEAKY_RELU, 0, false, UMNN_OPF_FP16>;
-    UMNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
-    if (narrow) UMNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int dev = 0, n_sm = 0;
+    UMNN_CUDA_TRY(current_device(&dev, &n_sm));
+    UMNN_CUDA_TRY(ensure_dynamic_smem(kern, dev, (int)S.total));      // through the memo: it must know what the attribute is
+    if (narrow) UMNN_CUDA_TRY(ensure_max_carveout(kern, dev));
     // the kernel is launched as clusters of 2: ask how many clusters the device holds at once
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2048);
@@ -866,10 +869,8 @@ int tc_forward_occupancy(const umnn_desc* d, int extra_rows, int* narrow_out, in
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    int n_clusters = 0, dev = 0, n_sm = 0;
+    int n_clusters = 0;
     UMNN_CUDA_TRY(cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfg));
-    UMNN_CUDA_TRY(cudaGetDevice(&dev));
-    UMNN_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     *ctas_per_sm = n_sm > 0 ? (2 * n_clusters) / n_sm : 0;
     return 0;
 }

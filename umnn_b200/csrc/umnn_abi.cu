@@ -1,5 +1,9 @@
 // extern "C" entry points declared in include/umnn_b200.h: argument validation, dispatch to the
 // kernels, error strings.  No torch types; plain pointers and sizes only.
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <utility>
 #include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
@@ -28,6 +32,69 @@ int cuda_fail(cudaError_t e, const char* what) {
     set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
     (void)cudaGetLastError();  // clear the sticky-free error state
     return (int)e;
+}
+
+namespace {
+struct LaunchMemo {
+    std::mutex mu;
+    std::map<int, int> n_sm;                                              // device -> SM count
+    std::map<std::pair<const void*, int>, int> smem;                      // (kernel, device) -> opted-in dynamic smem
+    std::map<std::pair<const void*, int>, bool> carveout;
+    std::map<std::tuple<const void*, int, int, size_t>, int> occ;
+};
+LaunchMemo& launch_memo() { static LaunchMemo m; return m; }
+}  // namespace
+
+cudaError_t current_device(int* dev, int* n_sm) {
+    cudaError_t e = cudaGetDevice(dev);
+    if (e != cudaSuccess) return e;
+    LaunchMemo& m = launch_memo();
+    std::lock_guard<std::mutex> lock(m.mu);
+    auto it = m.n_sm.find(*dev);
+    if (it == m.n_sm.end()) {
+        int n = 0;
+        e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, *dev);
+        if (e != cudaSuccess) return e;
+        it = m.n_sm.emplace(*dev, n).first;
+    }
+    *n_sm = it->second;
+    return cudaSuccess;
+}
+
+cudaError_t ensure_dynamic_smem(const void* kern, int dev, int bytes) {
+    LaunchMemo& m = launch_memo();
+    std::lock_guard<std::mutex> lock(m.mu);
+    int& have = m.smem[std::make_pair(kern, dev)];
+    if (bytes <= have) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) have = bytes;
+    return e;
+}
+
+cudaError_t ensure_max_carveout(const void* kern, int dev) {
+    LaunchMemo& m = launch_memo();
+    std::lock_guard<std::mutex> lock(m.mu);
+    bool& done = m.carveout[std::make_pair(kern, dev)];
+    if (done) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess) done = true;
+    return e;
+}
+
+cudaError_t cached_occupancy(int* occ, const void* kern, int dev, int threads, size_t smem) {
+    LaunchMemo& m = launch_memo();
+    std::lock_guard<std::mutex> lock(m.mu);
+    const auto key = std::make_tuple(kern, dev, threads, smem);
+    auto it = m.occ.find(key);
+    if (it == m.occ.end()) {
+        int n = 0;
+        const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smem);
+        if (e != cudaSuccess) return e;
+        if (m.occ.size() > 4096) m.occ.clear();
+        it = m.occ.emplace(key, n).first;
+    }
+    *occ = it->second;
+    return cudaSuccess;
 }
 
 int validate_desc(const umnn_desc* d) {

@@ -25,6 +25,20 @@ int cuda_fail(cudaError_t e, const char* what);
 
 int validate_desc(const umnn_desc* d);
 
+// ---------------------------------------------------------------------------------------------
+// Host-side memo of what the CUDA runtime would otherwise be asked on every launch (umnn_abi.cu).  A small call
+// (config 1: 5 100 rows, ~15 us on the GPU) spent more host time on cudaFuncSetAttribute, the occupancy query and
+// the device attribute lookups than on its two launches.
+// ---------------------------------------------------------------------------------------------
+// current device and its SM count
+cudaError_t current_device(int* dev, int* n_sm);
+// opt `kern` into `bytes` of dynamic shared memory on the current device unless it already is (monotonic)
+cudaError_t ensure_dynamic_smem(const void* kern, int dev, int bytes);
+// prefer the largest shared-memory carveout for `kern` (once per kernel and device)
+cudaError_t ensure_max_carveout(const void* kern, int dev);
+// cudaOccupancyMaxActiveBlocksPerMultiprocessor, memoised per (kernel, device, threads, smem)
+cudaError_t cached_occupancy(int* occ, const void* kern, int dev, int threads, size_t smem);
+
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 // ---------------------------------------------------------------------------------------------

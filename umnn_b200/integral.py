@@ -397,6 +397,20 @@ def cc_integrate(integrand, x0, x, h, nb_steps, want_fx=False, want_fx0=False, p
         return kernel.cc_forward(spec, x0, x, h, nb_steps, want_fx=want_fx, want_fx0=want_fx0, precision=precision)
 
 
+def prepare_integral(integrand, batch, nb_steps, n_dims=None, want_fx=False, want_fx0=False, device=None, precision=None):
+    """A `kernel.PreparedIntegral` for repeated value-only calls of ONE shape (serving loops, MonotonicNN at small
+    batch): `prep(x, h, x0=None)` returns what `cc_integrate(integrand, x0, x, h, nb_steps, ...)` returns, bit for bit,
+    with a fraction of the per-call host work.  Parameters are snapshotted: `prep.refresh()` after updating them."""
+    get_spec = getattr(integrand, "kernel_spec", None)
+    spec = get_spec() if callable(get_spec) else None
+    if spec is None:
+        raise ValueError("prepare_integral needs a recognised integrand (IntegrandNetwork, IntegrandNN, ContiguousIntegrand)")
+    if device is None:
+        device = spec.param_list[0].device
+    return kernel.PreparedIntegral(spec, batch, nb_steps, device, n_dims=n_dims, want_fx=want_fx, want_fx0=want_fx0,
+                                   precision=precision)
+
+
 def cc_integrate_host(integrand, x_host, h_host, nb_steps, want_fx=False, out=None, fx_out=None, device=None,
                       chunks=None, precision=None):
     """Host-buffer entry of the fused kernel: (pinned) host tensors in, host tensors out -> (integral, f(x,h) | None).
