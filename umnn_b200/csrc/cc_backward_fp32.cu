@@ -329,14 +329,30 @@ constexpr int kWP = kWT + 4;
 
 // 256 threads, 8 x 8 outputs each (n: tn*4..+3 and 64+tn*4..+3, k likewise) so every smem read is a
 // conflict-free float4; operands are transposed on the way in ([dim][rows] panels -> [r][dim] tiles)
-__global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ dz, const float* __restrict__ a, long long ld,
-                                                    long long rows, long long slab, int nout, int nin, float* __restrict__ part,
-                                                    long long part_stride, int w_dst, int b_dst, const int* __restrict__ run_if) {
+// All Linear layers of a chunk in ONE launch (blockIdx.x walks the output tiles of every layer): as the guarded re-run
+// of a tensor-core backward this sequence is a string of no-op launches (~2.7 us each), one per layer was 2/3 of them.
+struct WgradLayers {
+    int n_layers;
+    int tile_base[UMNN_MAX_LAYERS + 1];        // first output tile of layer l in blockIdx.x
+    int tiles_k[UMNN_MAX_LAYERS];              // tiles along k (inputs + bias column)
+    int nout[UMNN_MAX_LAYERS], nin[UMNN_MAX_LAYERS], w_dst[UMNN_MAX_LAYERS], b_dst[UMNN_MAX_LAYERS];
+    long long dz_off[UMNN_MAX_LAYERS], a_off[UMNN_MAX_LAYERS];   // panel offsets in the scratch (floats)
+};
+
+__global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ scratch, const __grid_constant__ WgradLayers W, long long ld,
+                                                    long long rows, long long slab, float* __restrict__ part,
+                                                    long long part_stride, const int* __restrict__ run_if) {
     if (run_if != nullptr && *run_if == 0) return;
     __shared__ __align__(16) float As[2][kWK][kWP];   // [stage][r][n]
     __shared__ __align__(16) float Bs[2][kWK][kWP];   // [stage][r][k]
     const int tid = threadIdx.x;
-    const int k0 = blockIdx.x * kWT, n0 = blockIdx.y * kWT;
+    int layer = 0;
+    while (layer + 1 < W.n_layers && (int)blockIdx.x >= W.tile_base[layer + 1]) ++layer;
+    const int tile = (int)blockIdx.x - W.tile_base[layer];
+    const int nout = W.nout[layer], nin = W.nin[layer], w_dst = W.w_dst[layer], b_dst = W.b_dst[layer];
+    const float* __restrict__ dz = scratch + W.dz_off[layer];
+    const float* __restrict__ a = scratch + W.a_off[layer];
+    const int k0 = (tile % W.tiles_k[layer]) * kWT, n0 = (tile / W.tiles_k[layer]) * kWT;
     const long long r_begin = (long long)blockIdx.z * slab;
     long long r_end = r_begin + slab;
     if (r_end > rows) r_end = rows;
@@ -594,12 +610,19 @@ int launch_backward_fp32(const umnn_desc* d, const float* x0, const float* x, co
             long long slab = (rows + nsplit - 1) / nsplit;
             slab = (slab + kWK - 1) / kWK * kWK;
             nsplit = (int)((rows + slab - 1) / slab);
+            WgradLayers W{};
+            W.n_layers = d->n_layers;
+            int n_tiles = 0;
             for (int l = 0; l < d->n_layers; ++l) {
-                dim3 g((L.nin[l] + 1 + kWT - 1) / kWT, (L.nout[l] + kWT - 1) / kWT, nsplit);
-                wgrad_kernel<<<g, 256, 0, s>>>(scratch + p.dz_panel[l], scratch + p.a_panel[l], B.ld, rows, slab, L.nout[l],
-                                                L.nin[l], part, B.P, L.src_w_off[l], L.src_b_off[l], run_if);
-                UMNN_CUDA_TRY(cudaGetLastError());
+                W.tile_base[l] = n_tiles;
+                W.tiles_k[l] = (L.nin[l] + 1 + kWT - 1) / kWT;
+                n_tiles += W.tiles_k[l] * ((L.nout[l] + kWT - 1) / kWT);
+                W.nout[l] = L.nout[l]; W.nin[l] = L.nin[l]; W.w_dst[l] = L.src_w_off[l]; W.b_dst[l] = L.src_b_off[l];
+                W.dz_off[l] = p.dz_panel[l]; W.a_off[l] = p.a_panel[l];
             }
+            W.tile_base[d->n_layers] = n_tiles;
+            wgrad_kernel<<<dim3((unsigned)n_tiles, 1, (unsigned)nsplit), 256, 0, s>>>(scratch, W, B.ld, rows, slab, part, B.P, run_if);
+            UMNN_CUDA_TRY(cudaGetLastError());
             reduce_partials_kernel<<<(unsigned)((B.P + 255) / 256), 256, 0, s>>>(part, B.P, nsplit, B.P, d_params, first ? 0 : 1, run_if);
             UMNN_CUDA_TRY(cudaGetLastError());
         }
