@@ -161,6 +161,7 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
     int* nodeid = reinterpret_cast<int*>(smem + p.S.off_node);        // [bufs][128]
     float* part = reinterpret_cast<float*>(smem + p.S.off_part);      // [3][128]
     float* fval = reinterpret_cast<float*>(smem + p.S.off_fval);      // [128]
+    float* carry2 = reinterpret_cast<float*>(smem + p.S.off_carry);   // [2]
     float* tab_t = reinterpret_cast<float*>(smem + p.S.off_tabt);
     float* tab_w = reinterpret_cast<float*>(smem + p.S.off_tabw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.S.off_bars);
@@ -390,7 +391,6 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
         const int pairs1 = (L.npad1 + 31) / 32, pairsL = (L.npadL + 31) / 32;
         const uint32_t col_last = ((n_mma - 1) & 1) ? kColQ : kColP;   // accumulator region of the last MMA layer
         const TcMmaLayer& ylast = L.layer[n_mma - 1];
-        float carry = 0.0f;
         float amax = 0.0f;     // largest |activation| this thread turned into an fp16 operand
 
         mbar_wait(&bars[BAR_WLOAD], 0, 130);
@@ -594,10 +594,16 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
                 }
             }
             epi_bar_sync<kEpiThreads>();
-            if (!EMIT && warp == 0 && row0 < n_rows_i) {
+            if (!EMIT && row0 < n_rows_i) {
+                // Per-slot node sums, one slot per warp (slot s_first + w, + kEpiWarps, ..).  With warp 0 doing all of them
+                // the next tile waited for it: every pair needs all four quadrant warps, and on narrow networks an MMA
+                // layer is shorter than this loop (half of warp 0's samples in the config-5 profile).  The slot that
+                // straddles two tiles hands its partial sum over through shared memory (double buffered: the warp
+                // that reads tile t's carry-in may run next to the one that writes its carry-out).  Same lanes, same
+                // order of additions as before: same bits.
                 const int last_row = (row0 + kTcTile < n_rows_i ? row0 + kTcTile : n_rows_i) - 1;
                 const int s_first = (int)((uint32_t)row0 / (uint32_t)p.rps), s_last = (int)((uint32_t)last_row / (uint32_t)p.rps);
-                for (int ls = s_first; ls <= s_last; ++ls) {
+                for (int ls = s_first + warp; ls <= s_last; ls += kEpiWarps) {
                     const int a = ls * p.rps, bb = a + p.Q;
                     const int lo = a > row0 ? a : row0;
                     const int hi = bb < last_row ? bb : last_row;
@@ -606,7 +612,7 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
                     if (lo <= hi) {
-                        const float total = (a < row0 ? carry : 0.0f) + sum;
+                        const float total = (a < row0 ? carry2[t & 1] : 0.0f) + sum;
                         if (bb <= last_row) {
                             if (lane == 0) {
                                 const long long slot = slot_begin + ls;
@@ -614,9 +620,8 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
                                 const float span = __fsub_rn(upper_limit(x0v, p.x[slot], p.Q), x0v);
                                 p.out[slot] = __fmul_rn(__fmul_rn(total, span), 0.5f);
                             }
-                            carry = 0.0f;
-                        } else {
-                            carry = total;
+                        } else if (lane == 0) {
+                            carry2[(t + 1) & 1] = total;
                         }
                     }
                 }

@@ -125,7 +125,7 @@ inline bool tc_layout_is_narrow(const TcLayout& L) {
 
 // dynamic shared memory map of the forward kernel (byte offsets from the 1024-aligned base)
 struct TcSmem {
-    uint32_t off_cvec, off_hbuf, off_xnode, off_lsrel, off_node, off_part, off_fval, off_tabt, off_tabw, off_bars, off_holder;
+    uint32_t off_cvec, off_hbuf, off_xnode, off_lsrel, off_node, off_part, off_fval, off_carry, off_tabt, off_tabw, off_bars, off_holder;
     uint32_t total;
     int max_slots;
     int h_stride;       // floats per slot row of hbuf: [h_0 .. h_{E-1}, 1.0, 0 ...], = round_up(E + 2, 16) = width of panel A_0
@@ -147,6 +147,7 @@ inline TcSmem make_tc_smem(const TcLayout& L, int rps, int Q) {
     S.off_node = off;   off += 4u * kTcPrepBufs * kTcTile;
     S.off_part = off;   off += 4u * 3 * kTcTile;
     S.off_fval = off;   off += 4u * kTcTile;
+    S.off_carry = off;  off += 16;          // partial node sum of the slot that straddles two tiles, double buffered
     S.off_tabt = off;   off += 4u * (Q + 1);
     S.off_tabw = off;   off += 4u * (Q + 1);
     off = (off + 7u) & ~7u;
