@@ -1,7 +1,7 @@
 #!/bin/bash
 # Turn the files a `scripts/gpu_round_r2.sh` visit merged into gpurun_out/r2final into the tracked evidence under profiles/.
 set -u
-SRC=gpurun_out/r2final
+SRC=gpurun_out/${1:-r2final}
 DST=profiles
 for wl in cfg1 cfg2 cfg3 cfg4 cfg5; do cp $SRC/bench_$wl.json $DST/r2_bench_$wl.json; done
 cp $SRC/bench_cfg4_fp32.json $DST/r2_bench_cfg4_fp32.json

@@ -3,7 +3,7 @@
 # and flow timings, gradient flip analysis, launch lists, ncu full captures (wide / narrow forward, the three backward passes),
 # compute-sanitizer memcheck.  Usage (under gpurun): bash scripts/gpu_round_r2.sh; then scripts/collect_r2_profiles.sh here.
 set -u
-OUT=gpurun_out/r2final
+OUT=gpurun_out/${1:-r2final}
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/gpu.txt 2>&1
 nproc > $OUT/nproc.txt
