@@ -71,6 +71,11 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  : "memory");
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"r"(kEpiThreads) : "memory"); }
+// producer / consumer barriers between the warps that park the input gradient in shared memory and the column group
+// that reduces it (PTX ISA, bar.arrive + bar.sync): 3 = "d0 full", 4 = "d0 empty"
+__device__ __forceinline__ void named_arrive(int id, int n_threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n_threads) : "memory"); }
+__device__ __forceinline__ void named_sync(int id, int n_threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory"); }
+constexpr int BARID_D0_FULL = 3, BARID_D0_EMPTY = 4;
 
 // the chain needs hi AND lo of dz for its own MMAs, so both exist in registers; the panel keeps `parts` of them
 __device__ __forceinline__ void emit16(const PanelRow& R, int col, const uint32_t (&o)[16], int parts) {
@@ -250,6 +255,7 @@ __global__ void __launch_bounds__(kThreads, 1) cc_dgrad_tc_kernel(const __grid_c
         const bool even_layers = (J & 1) == 0;
         const int PJ = L.P[J];
         const int pairsJ = (PJ + 31) / 32, pairs0 = L.n0pad / 32;
+        const int kRedBarThreads = 128 * (pairs0 + 1);      // the column groups that write d0 (pairs0 <= 2) + the one that reduces it
         const uint32_t col_last = ((J - 1) & 1) ? kColQ : kColP;
         const TcChainLayer& ylast = L.layer[J - 1];
 
@@ -349,70 +355,78 @@ __global__ void __launch_bounds__(kThreads, 1) cc_dgrad_tc_kernel(const __grid_c
                     tmem_ld16(taddr, v0);
                     tmem_ld16(taddr + 16, v1);
                     tmem_ld_wait();
+                    if (t > 0) named_sync(BARID_D0_EMPTY, kRedBarThreads);     // the previous tile's reduction has read d0
                     float* dst = d0 + r * d0_stride + 32 * pp;
 #pragma unroll
                     for (int i = 0; i < 16; ++i) { dst[i] = __uint_as_float(v0[i]); dst[16 + i] = __uint_as_float(v1[i]); }
+                    __threadfence_block();
+                    named_arrive(BARID_D0_FULL, kRedBarThreads);
                 } else if (even_layers) {
                     for (int s = 0; s < ylast.nseg; ++s) mbar_wait(&bars[BAR_ACC + (J - 1) * 2 + s], par, 320 + s);
                     tc_fence_after_sync();
                 }
                 if (even_layers && has_next && pp < pairsJ) head_pair(bn, t + 1, pp);
             }
-            epi_bar_sync();
-            if (!even_layers && has_next) {
-                for (int s = 0; s < ylast.nseg; ++s) mbar_wait(&bars[BAR_ACC + (J - 1) * 2 + s], par, 330 + s);
-                tc_fence_after_sync();
-                mbar_wait(&bars[BAR_PREP_FULL + bn], (uint32_t)(((t + 1) / kTcPrepBufs) & 1), 133);
-                for (int pp = cg; pp < pairsJ; pp += kColGroups) head_pair(bn, t + 1, pp);
+            if (!even_layers) {
+                // odd chains: the last accumulator lives in P, which MMA layer 0 of the next tile overwrites -> the head of
+                // the next tile is published only after the warps that read P have done so
+                epi_bar_sync();
+                if (has_next) {
+                    for (int s = 0; s < ylast.nseg; ++s) mbar_wait(&bars[BAR_ACC + (J - 1) * 2 + s], par, 330 + s);
+                    tc_fence_after_sync();
+                    mbar_wait(&bars[BAR_PREP_FULL + bn], (uint32_t)(((t + 1) / kTcPrepBufs) & 1), 133);
+                    for (int pp = cg; pp < pairsJ; pp += kColGroups) head_pair(bn, t + 1, pp);
+                }
             }
 
-            // ---- per-slot context gradient (carried across tiles), Leibniz terms, Jacobian-point term of d_x
-            const int row0 = t * kTcTile, n_rows_i = (int)n_rows;
-            if (row0 < n_rows_i) {
-                const int last_row = (row0 + kTcTile < n_rows_i ? row0 + kTcTile : n_rows_i) - 1;
-                const int s_first = (int)((uint32_t)row0 / (uint32_t)p.rps), s_last = (int)((uint32_t)last_row / (uint32_t)p.rps);
-                const int ns = s_last - s_first + 1;
-                const float* cin = carry + (t & 1) * p.E;
-                float* cout = carry + ((t + 1) & 1) * p.E;
-                // every (slot, e) sum is split over kRedParts neighbouring lanes (rows lo + part, lo + part + kRedParts, ..)
-                // and combined by shuffles in a fixed order: the serial chain of one thread per (slot, e) -- up to rps
-                // dependent shared loads and adds, with every other epilogue warp parked at the barrier below -- was 12 %
-                // of this kernel's time
-                constexpr int kRedParts = 4;
-                const int n_items = ns * p.E * kRedParts;
-                for (int idx0 = 0; idx0 < n_items; idx0 += kEpiThreads) {      // warp-uniform trip count (shuffles inside)
-                    const int idx = idx0 + tid;
-                    const bool on = idx < n_items;
-                    const int part = idx & (kRedParts - 1), ie = idx / kRedParts;
-                    const int i = on ? ie / p.E : 0, e = on ? ie - i * p.E : 0;
-                    const int ls = s_first + i;
-                    const int a = ls * p.rps, bb = a + p.rps - 1;
-                    const int lo = a > row0 ? a : row0;
-                    const int hi = bb < last_row ? bb : last_row;
-                    float sum = 0.0f;
-                    if (on)
-                        for (int rr = lo + part; rr <= hi; rr += kRedParts) sum += d0[(rr - row0) * d0_stride + 1 + e];
-                    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-                    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-                    if (on && part == 0) {
+            // ---- per-slot context gradient (carried across tiles), Leibniz terms, Jacobian-point term of d_x: the LAST
+            //      column group alone (it converts half as many pairs per layer as the others), behind the d0 full /
+            //      d0 empty barriers.  With every epilogue warp in this reduction and a CTA-wide barrier on either side
+            //      of it, the next tile's first accumulators waited for it (14 % of the kernel's stall samples).
+            if (cg == kColGroups - 1) {
+                named_sync(BARID_D0_FULL, kRedBarThreads);
+                const int rtid = tid - (kColGroups - 1) * 128;          // 0..127
+                const int row0 = t * kTcTile, n_rows_i = (int)n_rows;
+                if (row0 < n_rows_i) {
+                    const int last_row = (row0 + kTcTile < n_rows_i ? row0 + kTcTile : n_rows_i) - 1;
+                    const int s_first = (int)((uint32_t)row0 / (uint32_t)p.rps), s_last = (int)((uint32_t)last_row / (uint32_t)p.rps);
+                    const int ns = s_last - s_first + 1;
+                    const float* cin = carry + (t & 1) * p.E;
+                    float* cout = carry + ((t + 1) & 1) * p.E;
+                    // one (slot, e) sum per thread, four independent partial sums (rows mod 4) added in a fixed order;
+                    // neighbouring lanes read neighbouring floats of a d0 row
+                    for (int idx = rtid; idx < ns * p.E; idx += 128) {
+                        const int i = idx / p.E, e = idx - i * p.E;
+                        const int ls = s_first + i;
+                        const int a = ls * p.rps, bb = a + p.rps - 1;
+                        const int lo = a > row0 ? a : row0;
+                        const int hi = bb < last_row ? bb : last_row;
+                        const float* col = d0 + 1 + e - row0 * d0_stride;
+                        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+                        int rr = lo;
+                        for (; rr + 3 <= hi; rr += 4) {
+                            s0 += col[rr * d0_stride];
+                            s1 += col[(rr + 1) * d0_stride];
+                            s2 += col[(rr + 2) * d0_stride];
+                            s3 += col[(rr + 3) * d0_stride];
+                        }
+                        for (; rr <= hi; ++rr) s0 += col[rr * d0_stride];
+                        float sum = (s0 + s1) + (s2 + s3);
                         if (a < row0) sum += cin[e];
                         if (bb <= last_row) {
                             if (p.d_h) {
-                                const long long slot = slot_begin + ls;
                                 if (p.layout == UMNN_LAYOUT_STRIDED_D) {
                                     const uint32_t dd = d_begin + (uint32_t)ls, dn = dd / (uint32_t)p.D;   // 32-bit: see n_begin
                                     p.d_h[(n_begin + dn) * (long long)p.E * p.D + (long long)e * p.D + (dd - dn * (uint32_t)p.D)] = sum;
                                 } else {
-                                    p.d_h[slot * (long long)p.E + e] = sum;
+                                    p.d_h[(slot_begin + ls) * (long long)p.E + e] = sum;
                                 }
                             }
                         } else {
                             cout[e] = sum;
                         }
                     }
-                }
-                if (cg == 0) {
-                    const int node = nodeid[b * kTcTile + r];
+                    const int node = nodeid[b * kTcTile + r];          // r = this thread's row of the tile, as in every column group
                     if (node > p.Q) {
                         const long long slot = slot_begin + (uint32_t)(row0 + r) / (uint32_t)p.rps;
                         const float g = p.grad_out[slot];
@@ -423,8 +437,9 @@ __global__ void __launch_bounds__(kThreads, 1) cc_dgrad_tc_kernel(const __grid_c
                         }
                     }
                 }
+                __threadfence_block();
+                if (has_next) named_arrive(BARID_D0_EMPTY, kRedBarThreads);
             }
-            epi_bar_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[BAR_PREP_EMPTY + b]);
         }
