@@ -76,6 +76,12 @@ template <int N_THREADS>
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(N_THREADS) : "memory"); }
 template <int N_THREADS>
 __device__ __forceinline__ void prep_bar_sync() { asm volatile("bar.sync 2, %0;" ::"n"(N_THREADS) : "memory"); }
+// producer / consumer barriers of the finalize step (PTX ISA: bar.arrive + bar.sync)
+constexpr int BARID_FIN_FULL = 3, BARID_FIN_EMPTY = 4, BARID_FIN_GROUP = 5;
+template <int ID, int N_THREADS>
+__device__ __forceinline__ void named_sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(N_THREADS) : "memory"); }
+template <int ID, int N_THREADS>
+__device__ __forceinline__ void named_arrive() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(N_THREADS) : "memory"); }
 
 template <int HIDDEN_ACT>
 __device__ __forceinline__ float hact(float v) {
@@ -561,70 +567,87 @@ cc_forward_tc_kernel(const __grid_constant__ TcParams p) {
                 if (even_layers && has_next && pp < pairs1) l1_pair(bn, t + 1, pp);
             }
 
-            // ---- finalize the rows of this tile
-            if (cg > 0) part[(cg - 1) * kTcTile + r] = partial;
-            epi_bar_sync<kEpiThreads>();
-            if (!even_layers && has_next) {
+            // ---- finalize the rows of this tile: the LAST column group alone (it converts the fewest pairs per layer),
+            //      behind producer / consumer barriers ("partials full" / "partials empty").  The other column groups hand
+            //      over their partial dot products and go straight on to the next tile: with two CTA-wide barriers around
+            //      the finalize step every warp waited for it, and on narrow networks the first MMA layer of the next
+            //      tile is shorter than that wait.  Same order of additions as before: same bits.
+            constexpr int kFin = kColGroups - 1;
+            if (cg != kFin) {
+                if (t > 0) named_sync<BARID_FIN_EMPTY, kEpiThreads>();      // the previous tile's partials have been read
+                part[cg * kTcTile + r] = partial;
+                __threadfence_block();
+                named_arrive<BARID_FIN_FULL, kEpiThreads>();
+            }
+            if (!even_layers) {
                 // odd layer counts: the last accumulator lives in P, which MMA layer 0 of the next tile
                 // overwrites -> publish layer 1 of the next tile only after every warp has read P
-                for (int s = 0; s < ylast.nseg; ++s) mbar_wait(&bars[BAR_ACC + (n_mma - 1) * 2 + s], par, 330 + s);
-                tc_fence_after_sync();
-                mbar_wait(&bars[BAR_PREP_FULL + bn], (uint32_t)(((t + 1) / kTcPrepBufs) & 1), 133);
-                for (int pp = cg; pp < pairs1; pp += kColGroups) l1_pair(bn, t + 1, pp);
-            }
-            const int row0 = t * kTcTile;                     // 32-bit row arithmetic (see the prep warps)
-            const int n_rows_i = (int)n_rows;
-            if (cg == 0) {
-                const int node = nodeid[b * kTcTile + r];
-                float vtot = partial;
-#pragma unroll
-                for (int g = 1; g < kColGroups; ++g) vtot += part[(g - 1) * kTcTile + r];
-                if (EMIT) p.emit.v[cta_row0 + row0 + r] = node >= 0 ? vtot : 0.0f;
-                if (node >= 0) {
-                    // fp16 operands, LeakyReLU: an overflowed activation has made this row's output NaN (see kTrack)
-                    if (OPF == UMNN_OPF_FP16 && !kTrack && p.raise_flag != nullptr && !(fabsf(vtot) <= 3.0e38f)) *p.raise_flag = p.epoch;
-                    const float f = out_act(vtot, p.out_act);
-                    if (node <= p.Q) {
-                        fval[r] = f * tab_w[node];
-                    } else if (!EMIT) {
-                        const long long slot = slot_begin + (uint32_t)(row0 + r) / (uint32_t)p.rps;
-                        if (node == p.Q + 1 && p.x_row) p.out_fx[slot] = f;
-                        else p.out_fx0[slot] = f;
-                    }
+                epi_bar_sync<kEpiThreads>();
+                if (has_next) {
+                    for (int s = 0; s < ylast.nseg; ++s) mbar_wait(&bars[BAR_ACC + (n_mma - 1) * 2 + s], par, 330 + s);
+                    tc_fence_after_sync();
+                    mbar_wait(&bars[BAR_PREP_FULL + bn], (uint32_t)(((t + 1) / kTcPrepBufs) & 1), 133);
+                    for (int pp = cg; pp < pairs1; pp += kColGroups) l1_pair(bn, t + 1, pp);
                 }
             }
-            epi_bar_sync<kEpiThreads>();
-            if (!EMIT && row0 < n_rows_i) {
-                // Per-slot node sums, one slot per warp (slot s_first + w, + kEpiWarps, ..).  With warp 0 doing all of them
-                // the next tile waited for it: every pair needs all four quadrant warps, and on narrow networks an MMA
-                // layer is shorter than this loop (half of warp 0's samples in the config-5 profile).  The slot that
-                // straddles two tiles hands its partial sum over through shared memory (double buffered: the warp
-                // that reads tile t's carry-in may run next to the one that writes its carry-out).  Same lanes, same
-                // order of additions as before: same bits.
-                const int last_row = (row0 + kTcTile < n_rows_i ? row0 + kTcTile : n_rows_i) - 1;
-                const int s_first = (int)((uint32_t)row0 / (uint32_t)p.rps), s_last = (int)((uint32_t)last_row / (uint32_t)p.rps);
-                for (int ls = s_first + warp; ls <= s_last; ls += kEpiWarps) {
-                    const int a = ls * p.rps, bb = a + p.Q;
-                    const int lo = a > row0 ? a : row0;
-                    const int hi = bb < last_row ? bb : last_row;
-                    float sum = 0.0f;
-                    for (int rr = lo + lane; rr <= hi; rr += 32) sum += fval[rr - row0];
+            if (cg == kFin) {
+                named_sync<BARID_FIN_FULL, kEpiThreads>();
+                const int row0 = t * kTcTile;                     // 32-bit row arithmetic (see the prep warps)
+                const int n_rows_i = (int)n_rows;
+                {
+                    const int node = nodeid[b * kTcTile + r];
+                    float vtot = kColGroups > 1 ? part[r] : partial;                      // ((p_0 + p_1) + p_2) + p_3
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                    if (lo <= hi) {
-                        const float total = (a < row0 ? carry2[t & 1] : 0.0f) + sum;
-                        if (bb <= last_row) {
-                            if (lane == 0) {
-                                const long long slot = slot_begin + ls;
-                                const float x0v = p.x0 ? p.x0[slot] : 0.0f;
-                                const float span = __fsub_rn(upper_limit(x0v, p.x[slot], p.Q), x0v);
-                                p.out[slot] = __fmul_rn(__fmul_rn(total, span), 0.5f);
-                            }
-                        } else if (lane == 0) {
-                            carry2[(t + 1) & 1] = total;
+                    for (int g = 1; g < kFin; ++g) vtot += part[g * kTcTile + r];
+                    if (kColGroups > 1) vtot += partial;
+                    if (EMIT) p.emit.v[cta_row0 + row0 + r] = node >= 0 ? vtot : 0.0f;
+                    if (node >= 0) {
+                        // fp16 operands, LeakyReLU: an overflowed activation has made this row's output NaN (see kTrack)
+                        if (OPF == UMNN_OPF_FP16 && !kTrack && p.raise_flag != nullptr && !(fabsf(vtot) <= 3.0e38f)) *p.raise_flag = p.epoch;
+                        const float f = out_act(vtot, p.out_act);
+                        if (node <= p.Q) {
+                            fval[r] = f * tab_w[node];
+                        } else if (!EMIT) {
+                            const long long slot = slot_begin + (uint32_t)(row0 + r) / (uint32_t)p.rps;
+                            if (node == p.Q + 1 && p.x_row) p.out_fx[slot] = f;
+                            else p.out_fx0[slot] = f;
                         }
                     }
                 }
+                if (!EMIT) {
+                    named_sync<BARID_FIN_GROUP, 128>();           // fval of the whole tile is there (this group's 4 warps)
+                    if (row0 < n_rows_i) {
+                        // Per-slot node sums, one slot per warp of the group (slot s_first + q, + 4, ..).  The slot that
+                        // straddles two tiles hands its partial sum over through shared memory (double buffered: the
+                        // warp that reads tile t's carry-in may run next to the one that writes its carry-out).
+                        const int last_row = (row0 + kTcTile < n_rows_i ? row0 + kTcTile : n_rows_i) - 1;
+                        const int s_first = (int)((uint32_t)row0 / (uint32_t)p.rps), s_last = (int)((uint32_t)last_row / (uint32_t)p.rps);
+                        for (int ls = s_first + q; ls <= s_last; ls += 4) {
+                            const int a = ls * p.rps, bb = a + p.Q;
+                            const int lo = a > row0 ? a : row0;
+                            const int hi = bb < last_row ? bb : last_row;
+                            float sum = 0.0f;
+                            for (int rr = lo + lane; rr <= hi; rr += 32) sum += fval[rr - row0];
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                            if (lo <= hi) {
+                                const float total = (a < row0 ? carry2[t & 1] : 0.0f) + sum;
+                                if (bb <= last_row) {
+                                    if (lane == 0) {
+                                        const long long slot = slot_begin + ls;
+                                        const float x0v = p.x0 ? p.x0[slot] : 0.0f;
+                                        const float span = __fsub_rn(upper_limit(x0v, p.x[slot], p.Q), x0v);
+                                        p.out[slot] = __fmul_rn(__fmul_rn(total, span), 0.5f);
+                                    }
+                                } else if (lane == 0) {
+                                    carry2[(t + 1) & 1] = total;
+                                }
+                            }
+                        }
+                    }
+                }
+                __threadfence_block();
+                if (has_next) named_arrive<BARID_FIN_EMPTY, kEpiThreads>();
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[BAR_PREP_EMPTY + b]);
