@@ -8,6 +8,11 @@ from umnn_b200 import IntegrandNetwork, kernel, _native, cc_integrate
 
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 B, D, E, hidden, Q = 24, 3, 6, [40, 24, 24], 30
+if which == "multitile":
+    # several tiles per CTA in every tensor-core kernel (narrow forward: > 296 x 128 rows; wide passes F / D: > 148 x 128):
+    # the tile-to-tile hand-overs (prep buffers, "partials full / empty", "d0 full / empty", the straddling slot's carry)
+    # only exist from the second tile on
+    B = 700
 spec = orc.MLPSpec(tuple([1 + E] + hidden + [1]))
 flat = orc.synth_params(spec, 0, 1.5)
 x0, x, h, g = orc.synth_inputs(B, D, E * D, 1, x0_zero=False)
@@ -25,8 +30,8 @@ ref = orc.integrate_parallel(spec, flat, x0, x, h, Q)
 # fp16x3_hi: the same with hi-only operand panels and 3 blocks per pass-W stage (the large-batch configuration);
 # overflow: inputs that leave the fp16 range, so the guarded FP32 re-runs (forward and backward) really execute.
 for name, prec in (("fp32", _native.PREC_FP32), ("bf16x3", _native.PREC_BF16X3), ("fp16x3", _native.PREC_FP16X3),
-                   ("fp16x3_hi", _native.PREC_FP16X3), ("overflow", _native.PREC_FP16X3)):
-    if which not in ("all", name):
+                   ("fp16x3_hi", _native.PREC_FP16X3), ("overflow", _native.PREC_FP16X3), ("multitile", _native.PREC_FP16X3)):
+    if which not in ("all", name) or (which == "all" and name == "multitile"):
         continue
     if name == "fp16x3_hi":
         os.environ["UMNN_B200_BWD_PANELS"] = "hi"
