@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round 2, visit d (2 GPUs): NCCL training-step check, strong-scaled bench at N=2, reference arm under torchrun.
 set -u
-OUT=gpurun_out/r2d
+OUT=gpurun_out/${1:-r2d}
 mkdir -p $OUT
 nvidia-smi --query-gpu=index,name,clocks.sm,power.draw --format=csv > $OUT/gpu.txt 2>&1
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
