@@ -1,22 +1,25 @@
-// Tensor-core backward of the Clenshaw-Curtis integral (BF16x3 on tcgen05), three passes per chunk of rows.
+// Tensor-core backward of the Clenshaw-Curtis integral (tcgen05), three passes per chunk of rows.
 //
 // Replaces ParallelNeuralIntegral.backward (models/UMNN/ParallelNeuralIntegral.py:110-123),
 // integrate(compute_grad=True) (:66-80) and computeIntegrand (:83-94).
 //
 //   pass F  cc_forward_tc_kernel<.., EMIT=true> (cc_forward_tc.cu): re-evaluates the network for the chunk and
-//           writes the activation panels A_0..A_J (bf16 hi/lo, UMMA-tiled), their sign masks and v per row.
+//           writes the activation panels A_0..A_J (bf16 hi [and lo], UMMA-tiled), their sign masks (pair-major) and v per
+//           row; with fp16 operands by default, so that its signs are those of the forward that was differentiated.
 //   pass D  cc_dgrad_tc_kernel (here): the same persistent CTA-pair machinery run on the TRANSPOSED weights:
 //           dz_J = dv * w_out (.) act'(a_J) is rank-1 on CUDA cores, every further layer is
 //           da = dz . W (3 MMAs per K block, A operand in TMEM) followed by an in-place epilogue
 //           dz = da (.) act'(a) -> hi/lo; the last MMA layer yields d f / d input, reduced per slot into d_h
-//           (and the Jacobian-point term of d_x).  Emits the dz panels.
+//           (and the Jacobian-point term of d_x) by the last column group behind "d0 full / empty" named barriers.
+//           Emits the dz panels; the prep warps prefetch the tile's sign masks into L2.
 //   pass W  cc_wgrad_tc_kernel (here): dW_j = DZ_j^T A_{j-1} for every layer at once; the panels are ready-made
 //           MN-major UMMA tiles moved by bulk-TMA; every CTA pair reduces its slab of rows into TMEM
 //           accumulators (all layers resident: 464 of 512 columns at [200]^3) and writes one partial, summed
 //           in a fixed order by reduce_partials_tc_kernel.  Column H_{j-1} of A_{j-1} holds 1.0, so the bias
 //           gradient is one more column of the same GEMM.
 //
-// Scratch = panels of one chunk (5.3 KB per row at [200]^3), bounded by kBwdMaxTiles tiles per CTA.
+// Scratch = panels of one chunk (2.7 KB per row at [200]^3 with hi-only panels, 5.3 KB with hi + lo), bounded by
+// kBwdMaxTiles tiles per CTA.
 #include "tc_common.cuh"
 #include "tc_kernels.cuh"
 

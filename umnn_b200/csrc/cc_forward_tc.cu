@@ -1,14 +1,16 @@
-// Fused Clenshaw-Curtis forward, BF16x3 tensor-core path (UMNN_PREC_BF16X3) for sm_100a.
+// Fused Clenshaw-Curtis forward on tcgen05 for sm_100a: 16-bit hi/lo operand split (template parameter OPF: fp16 for
+// UMNN_PREC_FP16X3 -- the product path, guarded by a device flag and an FP32 re-run -- or bf16 for the diagnostic
+// UMNN_PREC_BF16X3).  With EMIT != 0 the same kernel is pass F of the tensor-core backward (cc_backward_tc.cu).
 //
 // One persistent CTA PAIR (cluster of 2, tcgen05 cta_group::2) per two SMs.  Every CTA owns a contiguous
 // range of whole slots and walks its (slot, node) rows in tiles of 128; the pair runs in lock-step so
 // one elected thread of the leader CTA issues every MMA for both (M = 256).
 //
-//   weights      all hidden-to-hidden matrices, split into bf16 hi + lo, live in SHARED MEMORY for the
+//   weights      all hidden-to-hidden matrices, split into hi + lo, live in SHARED MEMORY for the
 //                whole kernel (each CTA holds half of the N rows of every matrix; cta_group::2 reads
 //                both halves), staged once per CTA by a bulk-TMA copy.
 //   activations  live in TENSOR MEMORY only: region P = columns [0,256), Q = [256,512).  An MMA layer
-//                reads its A operand (bf16 hi/lo pairs) from one region and accumulates fp32 into the
+//                reads its A operand (hi/lo pairs) from one region and accumulates fp32 into the
 //                other; the epilogue converts the accumulator IN PLACE into the next layer's A operand
 //                (16 fp32 columns -> 8 hi + 8 lo packed columns), chunk by chunk, and the next layer's
 //                K-block MMAs start as soon as their chunk is converted.
@@ -17,9 +19,11 @@
 //   output layer dot product on CUDA cores while the last accumulator is read, ELU+1, CC weight,
 //                deterministic segmented sum per slot, (z*(xT-x0))/2.
 //
-// Warp roles per CTA (640 threads): warps 0-15 epilogue (TMEM lane quadrant = warp%4; warp/4 selects which
-// 32-column pairs of K blocks it converts), warps 16-18 "prep" (abscissae + c_slot, running tiles ahead),
-// warp 19 MMA issuer (one elected lane of the leader CTA).
+// Warp roles per CTA (wide shape, 640 threads): warps 0-15 epilogue (TMEM lane quadrant = warp%4; column group
+// warp/4 selects which 32-column pairs of K blocks it converts; the LAST column group also finalizes the tile's
+// rows, fed by the others through "partials full / empty" named barriers), warps 16-18 "prep" (context gather,
+// abscissae, c_slot and -- pass F -- the A_0 panel, running tiles ahead), warp 19 MMA issuer (converged warp,
+// uniform datapath, one elected lane of the leader CTA).  Narrow shape: 8 epilogue warps, two CTAs per SM.
 #include "tc_common.cuh"
 #include "tc_layout.cuh"
 #include "tc_bwd_layout.cuh"
