@@ -715,14 +715,28 @@ __global__ void reduce_partials_tc_kernel(const float* __restrict__ part, long l
 // host side
 // ------------------------------------------------------------------------------------------------------
 // UMNN_B200_BWD_PANELS = auto (default) | hi | a_hilo | hilo.  auto: hi-only panels once the call fills at least one
-// whole chunk of rows (148 CTAs x kBwdMaxTiles tiles: the regime where the scratch traffic costs time), hi + lo
+// whole 32-tile chunk of rows (kBwdHiOnlyRows: the regime where the scratch traffic costs time), hi + lo
 // below (small calls are latency bound, the second part is free there and keeps the weight gradient at fp32 grade).
+// Tiles of 128 rows per CTA and chunk.  Every chunk pays the prologues and tails of its four launches (weight staging,
+// tensor-memory allocation, cluster barriers, the last tile's drain), the gaps between them and -- through the size of
+// the workspace the guarded FP32 re-run borrows -- a share of that re-run's no-op launches.  Sweep on one box
+// (profiles/r2_bwd_chunk_sweep.txt; 32 / 64 / 96 / 128 tiles, balanced chunks): config 4 at 8192 samples 85.6 / 80.8 /
+// 79.7 / 78.2 ms, config 3 4.74 / 4.43 / 4.26 / 4.29 ms, config 5 4.21 / 3.95 / 3.83 / 3.71 ms.  Scratch: 2.7 KB per row
+// = 1.6 GB at 32 tiles, 4.9 GB at 96 (only calls that large allocate it).  UMNN_B200_BWD_TILES = 8..256 overrides.
+int bwd_max_tiles() {
+    if (const char* e = getenv("UMNN_B200_BWD_TILES")) {
+        const int v = atoi(e);
+        if (v >= 8 && v <= 256) return v;
+    }
+    return kBwdMaxTiles;
+}
+
 BwdPanels bwd_panels(long long total_rows) {
     const char* e = getenv("UMNN_B200_BWD_PANELS");
     if (e && strcmp(e, "hilo") == 0) return BwdPanels{2, 2};
     if (e && strcmp(e, "a_hilo") == 0) return BwdPanels{2, 1};
     if (e && strcmp(e, "hi") == 0) return BwdPanels{1, 1};
-    return total_rows >= 148LL * kBwdMaxTiles * kTcTile ? BwdPanels{1, 1} : BwdPanels{2, 2};
+    return total_rows >= kBwdHiOnlyRows ? BwdPanels{1, 1} : BwdPanels{2, 2};
 }
 
 struct BwdTcPlan {
@@ -780,17 +794,16 @@ const char* make_bwd_plan(const umnn_desc* d, BwdTcPlan* B) {
     n_cta = (n_cta + 1) / 2 * 2;
     if (n_cta < 2) n_cta = 2;
     B->n_cta = (int)n_cta;
-    long long s_max = ((long long)kBwdMaxTiles * kTcTile) / B->rps;     // slots that fit in the largest row block
+    long long s_max = ((long long)bwd_max_tiles() * kTcTile) / B->rps;  // slots that fit in the largest row block
     if (s_max < 1) return "a slot has more rows than one CTA's chunk (Q too large for the tensor-core backward)";
     const long long need = (n_slots + n_cta - 1) / n_cta;               // slots per CTA if everything went in one chunk
-    long long s_best = s_max < need ? s_max : need;
+    // Several chunks: BALANCED -- as many chunks as the largest row block demands, all of the same size.  With chunks
+    // of the maximum size and a remainder, the last chunk kept only part of the CTAs busy for a whole chunk's time
+    // (config 3: 5.25 chunks' worth of rows took 6 chunk times).
+    long long s_best = need;
     if (need > s_max) {
-        double best = 2.0;
-        for (long long sc = s_max; sc >= 1 && sc * 2 >= s_max; --sc) {
-            const long long rows_c = sc * B->rps;
-            const double waste = (double)((rows_c + kTcTile - 1) / kTcTile * kTcTile - rows_c) / (double)rows_c;
-            if (waste < best - 1e-9) { best = waste; s_best = sc; }
-        }
+        const long long n_chunks = (need + s_max - 1) / s_max;
+        s_best = (need + n_chunks - 1) / n_chunks;
     }
     if (s_best < 1) s_best = 1;
     B->slots_per_cta = s_best;

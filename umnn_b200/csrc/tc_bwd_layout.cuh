@@ -28,7 +28,8 @@
 namespace umnn {
 
 constexpr int kBwdMaxHidden = UMNN_MAX_LAYERS - 1;          // J <= 7
-constexpr int kBwdMaxTiles = 32;                            // tiles of 128 rows per CTA and chunk
+constexpr int kBwdMaxTiles = 96;                            // tiles of 128 rows per CTA and chunk (default; see bwd_max_tiles)
+constexpr long long kBwdHiOnlyRows = 148LL * 32 * 128;      // calls of at least this many rows use hi-only operand panels
 
 // bytes of one half-panel: r_pad rows (a multiple of 16) x W/2 columns x parts x 2 bytes
 __host__ __device__ inline size_t panel_half_bytes(long long r_pad, int W, int parts) { return (size_t)r_pad * (size_t)(W * parts); }

@@ -161,7 +161,8 @@ def _desc_info(spec: KernelSpec, desc: _native.Desc, what: str):
     dkey = getattr(desc, "_umnn_key", None)
     if dkey is None:        # a descriptor built elsewhere: ask the library directly
         return int(L.umnn_packed_layout_id(desc)) if what == "layout" else int(L.umnn_workspace_bytes(desc, 0 if what == "ws0" else 1))
-    env = (_env(b"UMNN_B200_TC_SEGMENTS"), _env(b"UMNN_B200_BWD_PANELS"), _env(b"UMNN_B200_TC_NARROW"), _env(b"UMNN_B200_WGRAD_KBS"))
+    env = (_env(b"UMNN_B200_TC_SEGMENTS"), _env(b"UMNN_B200_BWD_PANELS"), _env(b"UMNN_B200_TC_NARROW"), _env(b"UMNN_B200_WGRAD_KBS"),
+           _env(b"UMNN_B200_BWD_TILES"))
     key = (dkey, what, env)
     hit = spec.info_cache.get(key)
     if hit is not None:
