@@ -484,6 +484,35 @@ def test_native_backward_shapes(B, D, E, hidden, Q, layout, precision):
     assert_sum_grad_ok(got[2].cpu().numpy(), ref_flat.detach().cpu().numpy(), what="d_params vs torch ops")
 
 
+def test_weight_gradient_with_coherent_cotangents():
+    """A likelihood's cotangents are coherent: the Jacobian rows carry the same value (-1/(B f), f nearly constant at
+    initialisation), so the rank-1 head of the dgrad chain, dz_J = dv * w_out (.) act', holds the SAME number in every such
+    row and a hi-only bf16 panel rounds them all the same way -- the error does not average out over the rows (9e-3 of the last
+    hidden layer's weight gradient on a POWER-shaped flow, 1.3e-3 here with all-hi panels).  The default panels of a call this
+    large keep the lo part of the two head panels: every layer's weight gradient within 5e-4 of the FP32 backward's."""
+    from umnn_b200 import kernel, _native
+    B, D, E, hidden, Q = 4000, 6, 30, [200, 200, 200], 50          # 1.27 M rows: above the hi-only threshold
+    spec = orc.MLPSpec(tuple([1 + E] + hidden + [1]))
+    flat = orc.synth_params(spec, 0)
+    net = _net_for(spec, flat, "strided", D)
+    kspec = net.kernel_spec()
+    d = _dev()
+    g = torch.Generator(device=d).manual_seed(1)
+    x = 2 * torch.randn(B, D, device=d, generator=g)
+    h = torch.randn(B, E * D, device=d, generator=g)
+    x0 = torch.zeros_like(x)
+    go = torch.rand(B, D, device=d, generator=g) + 0.5
+    gfx = -torch.ones(B, D, device=d)
+    ref = kernel.cc_backward(kspec, x0, x, h, go, Q, grad_fx=gfx, precision=_native.PREC_FP32)[2].double()
+    got = kernel.cc_backward(kspec, x0, x, h, go, Q, grad_fx=gfx, precision=_native.PREC_FP16X3)[2].double()
+    off = 0
+    for p in net.parameters():
+        n = p.numel()
+        err = float((got[off:off + n] - ref[off:off + n]).norm() / ref[off:off + n].norm())
+        assert err < 5e-4, f"parameter of shape {tuple(p.shape)}: {err:.2e}"
+        off += n
+
+
 @pytest.mark.parametrize("layout,B,D,E,hidden,Q", [("contig", 100, 1, 2, [64, 64, 64], 50), ("strided", 37, 6, 30, [200, 200, 200], 50),
                                                   ("strided", 5, 3, 4, [24, 16], 7)])
 def test_prepared_integral_matches_generic_entry(layout, B, D, E, hidden, Q):

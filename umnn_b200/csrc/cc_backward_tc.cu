@@ -63,6 +63,7 @@ struct TcDgradParams {
     long long slot0, n_slots, slots_per_cta, row_block, r_pad;
     int tiles_per_cta, D, E, layout, Q, rps, out_act;
     int dz_parts;                              // parts of the dz panels: 1 = hi only, 2 = hi + lo
+    int dz_head_parts;                         // parts of DZ_J and DZ_{J+1} (see BwdPanels)
     const int* run_if;                         // not NULL: no-op unless *run_if != 0 (guarded bf16 re-run)
     TcDgradLayout L;
     TcDgradSmem S;
@@ -240,9 +241,9 @@ __global__ void __launch_bounds__(kThreads, 1) cc_dgrad_tc_kernel(const __grid_c
                 // dz_{J+1} panel (width 16): column 0 = dv
                 uint32_t hi, lo2;
                 split_bf16x2(dv, 0.0f, hi, lo2);
-                *reinterpret_cast<uint4*>(p.dz[J + 1] + panel_offset(pr, 0, 16, 0, p.dz_parts, p.r_pad)) = make_uint4(hi, 0u, 0u, 0u);
-                *reinterpret_cast<uint4*>(p.dz[J + 1] + panel_offset(pr, 8, 16, 0, p.dz_parts, p.r_pad)) = make_uint4(0u, 0u, 0u, 0u);
-                if (p.dz_parts == 2) {
+                *reinterpret_cast<uint4*>(p.dz[J + 1] + panel_offset(pr, 0, 16, 0, p.dz_head_parts, p.r_pad)) = make_uint4(hi, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(p.dz[J + 1] + panel_offset(pr, 8, 16, 0, p.dz_head_parts, p.r_pad)) = make_uint4(0u, 0u, 0u, 0u);
+                if (p.dz_head_parts == 2) {
                     *reinterpret_cast<uint4*>(p.dz[J + 1] + panel_offset(pr, 0, 16, 1, 2, p.r_pad)) = make_uint4(lo2, 0u, 0u, 0u);
                     *reinterpret_cast<uint4*>(p.dz[J + 1] + panel_offset(pr, 8, 16, 1, 2, p.r_pad)) = make_uint4(0u, 0u, 0u, 0u);
                 }
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(kThreads, 1) cc_dgrad_tc_kernel(const __grid_c
             const float dv = dvrow[bu * kTcTile + r];
             const uint32_t bits = p.mask[J][(long long)pp * p.r_pad + pr];
             const int halves = (32 * pp + 16 < PJ) ? 2 : 1;
-            const PanelRow prow = panel_row(p.dz[J], pr, PJ, p.dz_parts, p.r_pad);
+            const PanelRow prow = panel_row(p.dz[J], pr, PJ, p.dz_head_parts, p.r_pad);
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
                 if (hf < halves) {
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(kThreads, 1) cc_dgrad_tc_kernel(const __grid_c
                         split_bf16x2(z0, z1, o[i], o[8 + i]);
                     }
                     tmem_st16(tbase + lane_sel + kColQ + 32u * pp + 16u * hf, o);
-                    emit16(prow, 32 * pp + 16 * hf, o, p.dz_parts);
+                    emit16(prow, 32 * pp + 16 * hf, o, p.dz_head_parts);
                 }
             }
             tmem_st_wait();
@@ -714,9 +715,6 @@ __global__ void reduce_partials_tc_kernel(const float* __restrict__ part, long l
 // ------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------
-// UMNN_B200_BWD_PANELS = auto (default) | hi | a_hilo | hilo.  auto: hi-only panels once the call fills at least one
-// whole 32-tile chunk of rows (kBwdHiOnlyRows: the regime where the scratch traffic costs time), hi + lo
-// below (small calls are latency bound, the second part is free there and keeps the weight gradient at fp32 grade).
 // Tiles of 128 rows per CTA and chunk.  Every chunk pays the prologues and tails of its four launches (weight staging,
 // tensor-memory allocation, cluster barriers, the last tile's drain), the gaps between them and -- through the size of
 // the workspace the guarded FP32 re-run borrows -- a share of that re-run's no-op launches.  Sweep on one box
@@ -731,12 +729,17 @@ int bwd_max_tiles() {
     return kBwdMaxTiles;
 }
 
+// UMNN_B200_BWD_PANELS = auto (default) | hi_head | hi | a_hilo | hilo.  auto: hi-only panels -- except the two rank-1
+// head panels DZ_J and DZ_{J+1}, which keep their lo part (BwdPanels) -- once the call fills at least one whole 32-tile
+// chunk of rows (kBwdHiOnlyRows: the regime where the scratch traffic costs time), hi + lo everywhere below (small
+// calls are latency bound, the second part is free there and keeps the weight gradient at fp32 grade).
 BwdPanels bwd_panels(long long total_rows) {
     const char* e = getenv("UMNN_B200_BWD_PANELS");
-    if (e && strcmp(e, "hilo") == 0) return BwdPanels{2, 2};
-    if (e && strcmp(e, "a_hilo") == 0) return BwdPanels{2, 1};
-    if (e && strcmp(e, "hi") == 0) return BwdPanels{1, 1};
-    return total_rows >= kBwdHiOnlyRows ? BwdPanels{1, 1} : BwdPanels{2, 2};
+    if (e && strcmp(e, "hilo") == 0) return BwdPanels{2, 2, 2};
+    if (e && strcmp(e, "a_hilo") == 0) return BwdPanels{2, 1, 2};
+    if (e && strcmp(e, "hi_head") == 0) return BwdPanels{1, 1, 2};
+    if (e && strcmp(e, "hi") == 0) return BwdPanels{1, 1, 1};       // every panel hi-only: measurement only (see BwdPanels)
+    return total_rows >= kBwdHiOnlyRows ? BwdPanels{1, 1, 2} : BwdPanels{2, 2, 2};
 }
 
 struct BwdTcPlan {
@@ -905,6 +908,7 @@ int launch_backward_tc(const umnn_desc* d, const float* x0, const float* x, cons
     g.D = d->n_dims; g.E = d->n_ctx; g.layout = d->layout; g.Q = d->nb_steps; g.rps = B.rps; g.out_act = d->out_act;
     g.L = B.G; g.S = B.GS;
     g.dz_parts = B.panels.dz_parts;
+    g.dz_head_parts = B.panels.dz_head_parts;
     g.r_pad = B.R_pad;
 
     TcWgradParams w{};

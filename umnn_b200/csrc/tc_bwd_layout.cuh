@@ -175,8 +175,13 @@ struct TcWgradLayer {
 };
 
 // parts per element of the activation panels (A_0..A_J) and of the dz panels (DZ_1..DZ_{J+1}): 1 = bf16 hi only,
-// 2 = hi + lo.  UMNN_B200_BWD_PANELS = hi (default: {1,1}) | a_hilo ({2,1}) | hilo ({2,2}: round 1's scheme).
-struct BwdPanels { int a_parts, dz_parts; };
+// 2 = hi + lo.  UMNN_B200_BWD_PANELS = auto | hi_head ({1,1,2}) | hi ({1,1,1}) | a_hilo ({2,1,2}) | hilo ({2,2,2}: round 1's scheme).
+// dz_head_parts: parts of DZ_J (the rank-1 head dz_J = dv * w_out (.) act'(a_J)) and of DZ_{J+1} (= dv).  Their entries
+// are the SAME number for every row that shares dv -- the Jacobian rows of a likelihood have dv = -1/(B f) with f nearly
+// constant at initialisation -- so a hi-only panel rounds them all the same way and the error does not average out over
+// the rows: 9e-3 of the last hidden layer's weight gradient on a POWER-shaped flow (profiles/r2_panel_precision.txt).
+// These two panels therefore keep their lo part whenever the others drop it.
+struct BwdPanels { int a_parts, dz_parts, dz_head_parts; };
 
 struct TcWgradPlan {
     int n_layers;               // = J + 1
@@ -210,15 +215,18 @@ inline void tc_wgrad_set_stage(TcWgradPlan* W, int kbs) {
 inline int panel_A(int j) { return j; }                             // j = 0..J
 inline int panel_DZ(int j, int J) { return J + j; }                 // j = 1..J+1  -> J+1 .. 2J+1
 
-inline bool make_tc_wgrad_plan(const TcDgradLayout& G, TcWgradPlan* W, BwdPanels pp = BwdPanels{1, 1}) {
+inline bool make_tc_wgrad_plan(const TcDgradLayout& G, TcWgradPlan* W, BwdPanels pp = BwdPanels{1, 1, 2}) {
     *W = TcWgradPlan{};
     const int J = G.J;
     W->n_layers = J + 1;
     W->n_panels = 2 * J + 2;
     for (int j = 0; j <= J; ++j) { W->panel_width[panel_A(j)] = G.P[j]; W->panel_parts[panel_A(j)] = pp.a_parts; }
-    for (int j = 1; j <= J; ++j) { W->panel_width[panel_DZ(j, J)] = G.P[j]; W->panel_parts[panel_DZ(j, J)] = pp.dz_parts; }
+    for (int j = 1; j <= J; ++j) {
+        W->panel_width[panel_DZ(j, J)] = G.P[j];
+        W->panel_parts[panel_DZ(j, J)] = (j == J) ? pp.dz_head_parts : pp.dz_parts;
+    }
     W->panel_width[panel_DZ(J + 1, J)] = 16;
-    W->panel_parts[panel_DZ(J + 1, J)] = pp.dz_parts;
+    W->panel_parts[panel_DZ(J + 1, J)] = pp.dz_head_parts;
     int col = 0;
     for (int j = 1; j <= J + 1; ++j) {
         TcWgradLayer& y = W->layer[j - 1];
