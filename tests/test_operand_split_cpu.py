@@ -66,3 +66,38 @@ def test_fp16_reevaluation_flips_fewer_activation_kinks():
         flips[fmt] = sum(int(np.count_nonzero(a != b)) for a, b in zip(got[1:], exact))
     n_units = sum(e.size for e in exact)
     assert flips["bf16"] > 0 and flips["fp16"] * 4 < flips["bf16"], flips
+
+
+def test_hi_only_panels_average_out_unless_the_rows_are_coherent():
+    """Why the weight-gradient pass keeps the lo part of the two head panels (tc_bwd_layout.cuh:
+    BwdPanels).  dW = sum over rows of dz^T a with both operands rounded to bf16 ("hi-only" panels), exact accumulation:
+
+    * incoherent rows (every row its own dz): the rounding errors are independent and the error of the sum falls like
+      1/sqrt(rows);
+    * the rank-1 head dz_J = dv * w_out with the SAME dv in every row (a likelihood's Jacobian rows): every row rounds
+      dv * w_out[k] the same way, so the error of column k is the rounding error of that one number however many rows
+      are summed -- and a second (lo) part of dz removes it."""
+    rs = np.random.RandomState(0)
+    K, I = 64, 48
+    w_out = rs.standard_normal(K).astype(np.float32)
+    errs = {}
+    for n_rows in (1 << 10, 1 << 16):
+        a = np.abs(rs.standard_normal((n_rows, I))).astype(np.float32) + 0.5        # activations: same sign, no cancellation
+        for kind in ("incoherent", "coherent"):
+            dv = (rs.uniform(0.5, 1.5, (n_rows, 1)) if kind == "incoherent" else np.full((n_rows, 1), 0.7331)).astype(np.float32)
+            dz = (dv * w_out[None, :]).astype(np.float32)
+            exact = dz.astype(np.float64).T @ a.astype(np.float64)
+            a_hi = ops.round_bf16(a).astype(np.float64)
+            dz_hi, dz_lo = ops.split(dz, "bf16")
+            hi_only = dz_hi.astype(np.float64).T @ a_hi
+            hi_lo = (dz_hi.astype(np.float64) + dz_lo).T @ a_hi
+            nrm = np.linalg.norm(exact)
+            errs[(kind, n_rows, "hi")] = np.linalg.norm(hi_only - exact) / nrm
+            errs[(kind, n_rows, "hilo")] = np.linalg.norm(hi_lo - exact) / nrm
+    # independent rounding errors: 64 times the rows, ~8 times less error
+    assert errs[("incoherent", 1 << 16, "hi")] < 0.25 * errs[("incoherent", 1 << 10, "hi")]
+    assert errs[("incoherent", 1 << 16, "hi")] < 2e-5
+    # coherent rows: the error does not move with the number of rows and sits at the rounding error of one bf16 number
+    assert errs[("coherent", 1 << 16, "hi")] > 0.8 * errs[("coherent", 1 << 10, "hi")] > 2e-4
+    # ... until dz carries its lo part (what remains is the rounding of the activations, which does average out)
+    assert errs[("coherent", 1 << 16, "hilo")] < 2e-5
