@@ -451,6 +451,8 @@ def test_native_backward_matches_oracle(name, with_jac, precision):
     (257, 3, 4, [24, 16], 200, "strided"),              # slots longer than three tiles
     (1, 1, 1, [8], 1, "contig"),                        # tiny everything
     (50, 1, 255, [256, 256], 7, "contig"),              # widest input / hidden layers
+    (700, 3, 40, [64, 48], 20, "strided"),              # 32 < 1 + E <= 64: the input gradient spans two 32-column pairs (two
+                                                        # column groups park it for the d_h reduction), several tiles per CTA
 ])
 @pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
 def test_native_backward_shapes(B, D, E, hidden, Q, layout, precision):
