@@ -144,3 +144,31 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_native, "LIB_PATH", os.path.join(tmp_path, "nope.so"))
     with pytest.raises(RuntimeError, match="no CPU/eager fallback"):
         _native.lib()
+
+
+def test_backward_workspace_follows_the_chunk_plan(lib, monkeypatch):
+    """Host-only view of the tensor-core backward's chunk plan (cc_backward_tc.cu: make_bwd_plan) through the workspace
+    size it asks for: chunks are balanced (a call a little above one maximum chunk is cut into two equal chunks, not a full
+    one and a remainder), UMNN_B200_BWD_TILES bounds the chunk, and from 606 K rows on the panels are hi-only except the two
+    head panels (the all-hi measurement mode asks for less, hi + lo everywhere for more)."""
+    def ws(B, **env):
+        for k in ("UMNN_B200_BWD_TILES", "UMNN_B200_BWD_PANELS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        d = _native.make_desc(_native.LAYOUT_STRIDED_D, B, 6, 30, [31, 200, 200, 200, 1], _native.ACT_LEAKY_RELU,
+                              _native.OUT_ELU_PLUS_1, 50, _native.PREC_BF16X3)        # rows = B * 6 * 53
+        return int(lib.umnn_workspace_bytes(d, 1))
+
+    full96 = ws(60000)                                  # 19 M rows: chunks of the maximum size (96 tiles x 148 CTAs = 1.82 M rows)
+    assert ws(120000) == full96                         # the workspace is one chunk, however many chunks follow
+    assert 0.9 * full96 < 3 * ws(60000, UMNN_B200_BWD_TILES="32") < 1.1 * full96
+    # 1.1 maximum chunks' worth of rows -> two chunks of 0.55 each, not 1 + 0.1
+    one_and_a_bit = ws(6300)                            # 2.0 M rows
+    assert 0.5 * full96 < one_and_a_bit < 0.65 * full96
+    # panel modes on a call above the hi-only threshold
+    auto, all_hi, hilo = ws(10000), ws(10000, UMNN_B200_BWD_PANELS="hi"), ws(10000, UMNN_B200_BWD_PANELS="hilo")
+    assert ws(10000, UMNN_B200_BWD_PANELS="hi_head") == auto
+    assert all_hi < auto < hilo and auto < 1.25 * all_hi and hilo > 1.7 * all_hi
+    # below the threshold every panel keeps its lo part
+    assert ws(1000) == ws(1000, UMNN_B200_BWD_PANELS="hilo")
