@@ -34,4 +34,4 @@ rows = B * D * (Q + 3)
 fpe = 2 * sum(a * b for a, b in zip(spec.widths[:-1], spec.widths[1:]))
 print(f"{name}: backward {ms:.3f} ms, {rows} rows, {ms * 1e6 / rows:.3f} ns/row, algorithmic {3 * fpe * rows / (ms * 1e-3) / 1e12:.1f} TFLOP/s "
       f"[panels={os.environ.get('UMNN_B200_BWD_PANELS', 'auto')} kbs={os.environ.get('UMNN_B200_WGRAD_KBS', 'auto')} "
-      f"overlap={os.environ.get('UMNN_B200_BWD_OVERLAP', 'auto')} wsms={os.environ.get('UMNN_B200_BWD_WSMS', '24')}]", flush=True)
+      f"tiles={os.environ.get('UMNN_B200_BWD_TILES', '96')}]", flush=True)
