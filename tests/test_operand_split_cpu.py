@@ -101,3 +101,22 @@ def test_hi_only_panels_average_out_unless_the_rows_are_coherent():
     assert errs[("coherent", 1 << 16, "hi")] > 0.8 * errs[("coherent", 1 << 10, "hi")] > 2e-4
     # ... until dz carries its lo part (what remains is the rounding of the activations, which does average out)
     assert errs[("coherent", 1 << 16, "hilo")] < 2e-5
+
+
+def test_row_scaling_would_decorrelate_coherent_rounding():
+    """The cure DESIGN.md 8 item 2 names but does not build: scale row r of dz by a pseudo-random c_r in [1, 2) and row r of the
+    activations by 1 / c_r before rounding both to bf16.  Equal dz values then round differently from row to row, the products
+    are unchanged up to fp32 rounding of c * (1 / c), and the error of the sum averages out again -- without a lo part."""
+    rs = np.random.RandomState(1)
+    K, I, n_rows = 64, 48, 1 << 16
+    w_out = rs.standard_normal(K).astype(np.float32)
+    a = np.abs(rs.standard_normal((n_rows, I))).astype(np.float32) + 0.5
+    dz = (np.full((n_rows, 1), 0.7331, np.float32) * w_out[None, :]).astype(np.float32)
+    exact = dz.astype(np.float64).T @ a.astype(np.float64)
+    plain = ops.round_bf16(dz).astype(np.float64).T @ ops.round_bf16(a).astype(np.float64)
+    c = (1.0 + rs.randint(0, 1 << 16, (n_rows, 1)) / 65536.0).astype(np.float32)
+    inv_c = (np.float32(1.0) / c).astype(np.float32)
+    scaled = ops.round_bf16((dz * c).astype(np.float32)).astype(np.float64).T @ ops.round_bf16((a * inv_c).astype(np.float32)).astype(np.float64)
+    nrm = np.linalg.norm(exact)
+    e_plain, e_scaled = np.linalg.norm(plain - exact) / nrm, np.linalg.norm(scaled - exact) / nrm
+    assert e_plain > 2e-4 and e_scaled < 0.1 * e_plain and e_scaled < 3e-5
